@@ -1,0 +1,143 @@
+/*
+ * padel_b200.h — C ABI of libpadel_b200.so: the B200 (sm_100a) per-frame inference engine that replaces the
+ * model forwards of the four padel_analytics trackers.
+ *
+ * The reference (pure Python) has no FFI; its "plugin boundary" is the duck-typed model object each tracker holds:
+ *   - YOLO trackers: self.model.predict(list_of_images, conf=, iou=, imgsz=, classes=, max_det=)
+ *       trackers/players_tracker/players_tracker.py:303,351-359
+ *       trackers/players_keypoints_tracker/players_keypoints_tracker.py:238,285-292
+ *       trackers/keypoints_tracker/keypoints_tracker.py:169,238-245
+ *   - Ball tracker: self.tracknet(x) + ensemble + heatmap->xy
+ *       trackers/ball_tracker/ball_tracker.py:260-266,439-523 ; predict.py:7-39,149-221 ; iterable.py:167-199
+ * Every entry point below takes plain device/host pointers, sizes and a cudaStream_t (as void*); no torch types.
+ * The Python host side (padel_analytics_b200/engine/*.py) binds them with ctypes and mirrors the reference's
+ * predict()/__call__ API above them.  See INTEGRATION.md for the reference-side stub a maintainer would add.
+ *
+ * Conventions
+ *   - Activations are NHWC, IEEE fp16 ("half"), channel counts padded to multiples of 16 with zero channels.
+ *   - All functions return 0 on success; on failure they return non-zero and pb_last_error() describes it.
+ *   - All launches go to the stream passed in; nothing synchronises unless documented.
+ */
+#ifndef PADEL_B200_H
+#define PADEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_ACT_NONE 0
+#define PB_ACT_RELU 1
+#define PB_ACT_SILU 2
+#define PB_ACT_SIGMOID 3
+
+#define PB_OUT_F16_NHWC 0     /* half, channel slice [out_coff, out_coff+cout_pad) of an NHWC tensor           */
+#define PB_OUT_F16_NHWC_UP2 1 /* same, each pixel replicated 2x2 into a (2Ho, 2Wo) tensor (nearest upsample)  */
+#define PB_OUT_F32_NHWC 2     /* float, channels [out_coff, out_coff+cout_store) of an NHWC float tensor       */
+#define PB_OUT_F32_NCHW 3     /* float, planar (N, cout_store, Ho, Wo)                                         */
+
+const char* pb_last_error(void);
+int pb_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+long long pb_launch_count(void);
+
+/* ---- fused conv + bias + activation (+ residual) : implicit GEMM on tcgen05 tensor cores ------------------
+ * Replaces ultralytics Conv (Conv2d+BN+SiLU, BN folded) and TrackNet Conv2DBlock (models.py:5-17).          */
+typedef struct pb_conv_desc {
+  const void* in;  /* half NHWC (N,H,W,C)                                        */
+  int N, H, W, C;  /* C = channel stride of the input tensor (multiple of 8)     */
+  int c_in_off;    /* first input channel read                                   */
+  int cin;         /* channels read (multiple of 16; zero-padded weights beyond the real count) */
+  const void* weight; /* half [taps][cout_pad][cin], taps = ksize*ksize, tap = r*ksize+s       */
+  const float* bias;  /* float [cout_pad] (folded BN shift or conv bias)                       */
+  int cout_pad;       /* multiple of 16                                                        */
+  int ksize;          /* 1 or 3 (padding = ksize/2)                                            */
+  int stride;         /* 1 or 2 (stride 2 needs even H and W)                                  */
+  int act;            /* PB_ACT_*                                                              */
+  const void* res;    /* optional half NHWC residual added after the activation, or NULL       */
+  int res_C, res_coff;
+  void* out;
+  int out_C;      /* channel stride of the output tensor (elements)                            */
+  int out_coff;   /* first output channel written                                              */
+  int out_mode;   /* PB_OUT_*                                                                  */
+  int cout_store; /* channels actually stored (<= cout_pad); f16 modes require a multiple of 8 */
+} pb_conv_desc;
+
+/* One-shot launches (plan + run). The *_reference variant is a plain CUDA-core kernel used by tests to
+ * cross-check the tensor-core kernel on the device; it is never used by the engines.                         */
+int pb_conv2d(const pb_conv_desc* d, void* stream);
+int pb_conv2d_reference(const pb_conv_desc* d, void* stream);
+
+/* ---- programs: an ordered list of device ops over caller-owned buffers, replayed with one call ------------ */
+typedef struct pb_program pb_program;
+pb_program* pb_program_create(void);
+void pb_program_destroy(pb_program* p);
+int pb_program_add_conv(pb_program* p, const pb_conv_desc* d);
+/* 2x2/s2 max-pool of a channel slice (TrackNet models.py:60,62,64) */
+int pb_program_add_maxpool2(pb_program* p, const void* in, int N, int H, int W, int C, int c_off, int c,
+                            void* out, int out_C, int out_coff);
+/* nearest x2 upsample of a channel slice into a slice of a (2H,2W) tensor (models.py:66,68,70; YOLO layers 10,13) */
+int pb_program_add_upsample2(pb_program* p, const void* in, int N, int H, int W, int C, int c_off, int c,
+                             void* out, int out_C, int out_coff);
+/* SPPF pooling: slice0=[0,c) of buf is x'; writes maxpool5, maxpool5^2, maxpool5^3 into slices 1..3 */
+int pb_program_add_sppf_pool(pb_program* p, void* buf, int N, int H, int W, int C, int c);
+int pb_program_num_ops(const pb_program* p);
+int pb_program_run(pb_program* p, void* stream);
+/* Run ops [first, last) only (per-layer timing / debugging). */
+int pb_program_run_range(pb_program* p, int first, int last, void* stream);
+
+/* ---- pre-processing --------------------------------------------------------------------------------------- */
+/* cv2.resize(INTER_LINEAR) + copyMakeBorder(114) + channel pick + /255 -> half NHWC with 16 channels (3 real).
+ * Bit-exact restatement of OpenCV's 11-bit fixed-point bilinear (ultralytics LetterBox).
+ * src: u8 (B,Hs,Ws,3). The resized area (rh,rw) is placed at (top,left) inside (Hn,Wn); everything else is 114.
+ * xofs int32[rw], xcoef int32[rw][2], yofs int32[rh], ycoef int32[rh][2]: per-axis source index and 11-bit
+ * coefficient pairs computed on the host exactly as cv::resize does. If rh==Hs and rw==Ws the copy is verbatim.
+ * (c0,c1,c2): source channel feeding network channel 0,1,2.                                                    */
+int pb_letterbox_u8_f16(const uint8_t* src, int B, int Hs, int Ws, void* dst, int Hn, int Wn, int rh, int rw,
+                        int top, int left, const int32_t* xofs, const int32_t* xcoef, const int32_t* yofs,
+                        const int32_t* ycoef, int c0, int c1, int c2, void* stream);
+/* Pillow Image.resize (BICUBIC, reducing_gap=None) two-pass fixed-point resample, bit-exact.
+ * Coefficients are computed on the host exactly as Pillow does (precompute_coeffs) and passed in:
+ *   bounds_*: int32 [out][2] = (xmin, xsize); kk_*: int32 [out][ksize] (22-bit fixed point).
+ * src u8 (B,Hs,Ws,3) -> tmp u8 (B,Hs,Wo,3) -> dst u8 (B,Ho,Wo,3). swap_rb!=0 swaps channels 0/2 on read (BGR->RGB). */
+int pb_pil_resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* tmp, uint8_t* dst, int Ho, int Wo,
+                     const int32_t* bounds_h, const int32_t* kk_h, int ksize_h, const int32_t* bounds_v,
+                     const int32_t* kk_v, int ksize_v, int swap_rb, void* stream);
+/* u8 (B,H,W,3) -> half NHWC (B,H,W,16): dst[...,k] = src[..., ck]/255 for k<3, 0 otherwise */
+int pb_u8_to_f16_nhwc16(const uint8_t* src, int B, int H, int W, void* dst, int c0, int c1, int c2, void* stream);
+/* TrackNet window assembly (iterable.py:167-199): frames u8 ring (T,H,W,3) RGB, median u8 (H,W,3) RGB ->
+ * x half NHWC (B,H,W,32): channels [med(3), f[first+b+0](3) ... f[first+b+7](3), 0 x5], value/255.              */
+int pb_tracknet_pack_windows(const uint8_t* frames, int ring, int first_slot, const uint8_t* median, int B, int H,
+                             int W, void* x, void* stream);
+
+/* ---- YOLOv8 head decode + NMS (ultralytics Detect/Pose decode, ops.non_max_suppression) --- */
+typedef struct pb_yolo_level {
+  const float* feat; /* float NHWC (B, h, w, fC): [0,64) DFL logits, [64,64+nc) class logits, [64+nc, +nk) kpts */
+  int h, w, stride;
+} pb_yolo_level;
+/* cand: float (B, cap, 6+nk) rows = x1,y1,x2,y2,conf,cls,kpts(raw decoded, network px); cand_count: int (B).
+ * Candidates are those with max class score > conf and (class_filter<0 or best class == class_filter).         */
+int pb_yolo_decode(const pb_yolo_level* levels, int nlevels, int B, int fC, int nc, int nk, int kdim, float conf,
+                   int class_filter, float* cand, int* cand_anchor, int* cand_count, int cap, void* stream);
+/* Per-image: sort by (conf desc, anchor asc), greedy NMS with IoU > iou suppression on class-offset boxes
+ * (offset 7680*cls), keep first max_det. out: float (B, max_det, 6+nk); out_count int (B).                      */
+int pb_yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count, int B, int cap, int rowlen,
+                float iou, int max_det, float* out, int* out_count, void* stream);
+
+/* ---- TrackNet post-processing (ball_tracker.py:449-509 ; predict.py:7-39) ---------------------------------- */
+/* Temporal ensemble + >thr. pred: float (S,8,H,W) raw heat-maps of consecutive windows; window index of pred[0]
+ * is `first_window`; frames [frame0, frame0+nframes) are produced; total_windows = total_frames-7.
+ * mask: u8 (nframes,H,W) (0/1). ens (optional, may be NULL): float (nframes,H,W).                               */
+int pb_tracknet_ensemble(const float* pred, int S, int first_window, int total_windows, int frame0, int nframes,
+                         int H, int W, float thr, uint8_t* mask, float* ens, void* stream);
+/* 8-connected components of each mask; picks the component with max bbox area (ties: the one whose first pixel in
+ * raster order comes last, = cv2.findContours order + predict_location's strict '>' scan).
+ * bbox: int (nframes,4) = x,y,w,h (0,0,0,0 if empty). scratch: int32 (nframes, 5, H*W).                          */
+int pb_ccl_bbox(const uint8_t* mask, int nframes, int H, int W, int* scratch, int* bbox, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PADEL_B200_H */

@@ -1,0 +1,101 @@
+"""ctypes binding of libpadel_b200.so (the C ABI declared in include/padel_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libpadel_b200.so"
+
+
+class PbError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("in_", C.c_void_p),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+        ("c_in_off", C.c_int), ("cin", C.c_int),
+        ("weight", C.c_void_p), ("bias", C.c_void_p),
+        ("cout_pad", C.c_int), ("ksize", C.c_int), ("stride", C.c_int), ("act", C.c_int),
+        ("res", C.c_void_p), ("res_C", C.c_int), ("res_coff", C.c_int),
+        ("out", C.c_void_p), ("out_C", C.c_int), ("out_coff", C.c_int), ("out_mode", C.c_int),
+        ("cout_store", C.c_int),
+    ]
+
+
+class YoloLevel(C.Structure):
+    _fields_ = [("feat", C.c_void_p), ("h", C.c_int), ("w", C.c_int), ("stride", C.c_int)]
+
+
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_SIGMOID = 0, 1, 2, 3
+OUT_F16_NHWC, OUT_F16_NHWC_UP2, OUT_F32_NHWC, OUT_F32_NCHW = 0, 1, 2, 3
+
+# name -> (restype, argtypes); must list every symbol of include/padel_b200.h (tests check this)
+_i, _p, _f = C.c_int, C.c_void_p, C.c_float
+SIGNATURES = {
+    "pb_last_error": (C.c_char_p, []),
+    "pb_version": (_i, []),
+    "pb_launch_count": (C.c_longlong, []),
+    "pb_conv2d": (_i, [C.POINTER(ConvDesc), _p]),
+    "pb_conv2d_reference": (_i, [C.POINTER(ConvDesc), _p]),
+    "pb_program_create": (_p, []),
+    "pb_program_destroy": (None, [_p]),
+    "pb_program_add_conv": (_i, [_p, C.POINTER(ConvDesc)]),
+    "pb_program_add_maxpool2": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i]),
+    "pb_program_add_upsample2": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i]),
+    "pb_program_add_sppf_pool": (_i, [_p, _p, _i, _i, _i, _i, _i]),
+    "pb_program_num_ops": (_i, [_p]),
+    "pb_program_run": (_i, [_p, _p]),
+    "pb_program_run_range": (_i, [_p, _i, _i, _p]),
+    "pb_letterbox_u8_f16": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "pb_pil_resize_u8": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _i, _i, _p]),
+    "pb_u8_to_f16_nhwc16": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p]),
+    "pb_tracknet_pack_windows": (_i, [_p, _i, _i, _p, _i, _i, _i, _p, _p]),
+    "pb_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _i, _p]),
+    "pb_yolo_nms": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p, _p]),
+    "pb_tracknet_ensemble": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p]),
+    "pb_ccl_bbox": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once). Raises PbError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise PbError(
+                f"{LIB_PATH} not found: build it with `python -m padel_analytics_b200.build` "
+                "(no CPU fallback exists)")
+        l = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(l, name)
+            except AttributeError:  # TEMP during bring-up
+                continue
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise PbError(lib().pb_last_error().decode())
+
+
+def ptr(t) -> int:
+    """Device/host pointer of a torch tensor (or None)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,138 @@
+// HBM-bound helper kernels on NHWC fp16 channel slices: 2x2 max-pool, nearest x2 upsample, SPPF pooling.
+// All move 16-byte vectors (8 channels) per thread with consecutive threads on consecutive channel groups,
+// so warps read/write contiguous NHWC runs.
+#include "internal.h"
+
+namespace pb {
+
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+  uint4 r;
+  const __half2* x = reinterpret_cast<const __half2*>(&a);
+  const __half2* y = reinterpret_cast<const __half2*>(&b);
+  __half2* z = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z[i] = __hmax2(x[i], y[i]);
+  return r;
+}
+
+// TrackNet nn.MaxPool2d((2,2), stride=(2,2)) — /root/reference/trackers/ball_tracker/models.py:60,62,64
+__global__ void maxpool2_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int c_off, int cg,
+                                __half* __restrict__ out, int out_C, int out_coff) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long total = (long)N * Ho * Wo * cg;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long p = i / cg;
+    const int ow = (int)(p % Wo);
+    const int oh = (int)((p / Wo) % Ho);
+    const int n = (int)(p / ((long)Wo * Ho));
+    const __half* b = in + (((size_t)n * H + 2 * oh) * W + 2 * ow) * C + c_off + g * 8;
+    const uint4 v00 = *reinterpret_cast<const uint4*>(b);
+    const uint4 v01 = *reinterpret_cast<const uint4*>(b + C);
+    const uint4 v10 = *reinterpret_cast<const uint4*>(b + (size_t)W * C);
+    const uint4 v11 = *reinterpret_cast<const uint4*>(b + (size_t)W * C + C);
+    *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oh) * Wo + ow) * out_C + out_coff + g * 8) =
+        hmax8(hmax8(v00, v01), hmax8(v10, v11));
+  }
+}
+
+// nn.Upsample(scale_factor=2) (nearest) — models.py:66,68,70 ; ultralytics layers 10/13
+__global__ void upsample2_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int c_off, int cg,
+                                 __half* __restrict__ out, int out_C, int out_coff) {
+  const int Ho = H * 2, Wo = W * 2;
+  const long total = (long)N * Ho * Wo * cg;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long p = i / cg;
+    const int ow = (int)(p % Wo);
+    const int oh = (int)((p / Wo) % Ho);
+    const int n = (int)(p / ((long)Wo * Ho));
+    const uint4 v =
+        *reinterpret_cast<const uint4*>(in + (((size_t)n * H + oh / 2) * W + ow / 2) * C + c_off + g * 8);
+    *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oh) * Wo + ow) * out_C + out_coff + g * 8) = v;
+  }
+}
+
+// SPPF: y1 = mp5(x'), y2 = mp5(y1), y3 = mp5(y2) with MaxPool2d(5,1,2) (-inf padding) == windows 5, 9, 13 of x'.
+// buf is the concat buffer (N,H,W,C=4c): slice 0 holds x', slices 1..3 are written.
+__global__ void sppf_pool_kernel(__half* __restrict__ buf, int N, int H, int W, int C, int cg) {
+  const long total = (long)N * H * W * cg;
+  const int c = cg * 8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long p = i / cg;
+    const int w = (int)(p % W);
+    const int h = (int)((p / W) % H);
+    const int n = (int)(p / ((long)W * H));
+    const __half ninf = __ushort_as_half((unsigned short)0xFC00);
+    uint4 m5, m9, m13;
+    {
+      __half2 t = __halves2half2(ninf, ninf);
+      uint4 init;
+      __half2* z = reinterpret_cast<__half2*>(&init);
+      z[0] = z[1] = z[2] = z[3] = t;
+      m5 = m9 = m13 = init;
+    }
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int y = h + dy;
+      if (y < 0 || y >= H) continue;
+      for (int dx = -6; dx <= 6; ++dx) {
+        const int x = w + dx;
+        if (x < 0 || x >= W) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(buf + (((size_t)n * H + y) * W + x) * C + g * 8);
+        m13 = hmax8(m13, v);
+        const int ay = dy < 0 ? -dy : dy, ax = dx < 0 ? -dx : dx;
+        if (ay <= 4 && ax <= 4) m9 = hmax8(m9, v);
+        if (ay <= 2 && ax <= 2) m5 = hmax8(m5, v);
+      }
+    }
+    __half* o = buf + (((size_t)n * H + h) * W + w) * C + g * 8;
+    *reinterpret_cast<uint4*>(o + c) = m5;
+    *reinterpret_cast<uint4*>(o + 2 * c) = m9;
+    *reinterpret_cast<uint4*>(o + 3 * c) = m13;
+  }
+}
+
+static int grid_for(long total, int threads) {
+  long b = (total + threads - 1) / threads;
+  const long cap = (long)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int launch_maxpool2(const void* in, int N, int H, int W, int C, int c_off, int c, void* out, int out_C,
+                    int out_coff, cudaStream_t s) {
+  PB_CHECK(c % 8 == 0 && c_off % 8 == 0 && C % 8 == 0 && out_C % 8 == 0 && out_coff % 8 == 0,
+           "maxpool2: channel slices must be multiples of 8");
+  PB_CHECK(H % 2 == 0 && W % 2 == 0, "maxpool2: odd spatial size");
+  const long total = (long)N * (H / 2) * (W / 2) * (c / 8);
+  maxpool2_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __half*>(in), N, H, W, C, c_off,
+                                                       c / 8, reinterpret_cast<__half*>(out), out_C, out_coff);
+  PB_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int launch_upsample2(const void* in, int N, int H, int W, int C, int c_off, int c, void* out, int out_C,
+                     int out_coff, cudaStream_t s) {
+  PB_CHECK(c % 8 == 0 && c_off % 8 == 0 && C % 8 == 0 && out_C % 8 == 0 && out_coff % 8 == 0,
+           "upsample2: channel slices must be multiples of 8");
+  const long total = (long)N * (H * 2) * (W * 2) * (c / 8);
+  upsample2_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __half*>(in), N, H, W, C, c_off,
+                                                        c / 8, reinterpret_cast<__half*>(out), out_C, out_coff);
+  PB_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int launch_sppf_pool(void* buf, int N, int H, int W, int C, int c, cudaStream_t s) {
+  PB_CHECK(c % 8 == 0 && C >= 4 * c && C % 8 == 0, "sppf: bad channel layout");
+  const long total = (long)N * H * W * (c / 8);
+  sppf_pool_kernel<<<grid_for(total, 128), 128, 0, s>>>(reinterpret_cast<__half*>(buf), N, H, W, C, c / 8);
+  PB_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace pb

@@ -1,0 +1,508 @@
+// Fused conv(k1|k3, s1|s2) + bias + activation (+ residual) as an implicit GEMM on Blackwell tensor cores.
+//
+//   D[M = 128 output pixels, N = BN out-channels] += A[M, K] * B[N, K]^T,   K = taps x input channels
+//
+// * A (activations, NHWC fp16) is fetched by TMA in tiled mode: one box = a (TN x TH x TW) patch of pixels x KB
+//   channels, shifted by the filter tap; out-of-bounds coordinates are zero-filled by TMA, which implements the
+//   conv zero padding for free.  Stride-2 convs read a 5-D view (N, H/2, 2, W/2, 2C) of the same tensor so every
+//   tap is again a dense box.  The box lands in shared memory directly in the UMMA K-major swizzled layout
+//   (one pixel = one KB*2-byte row; swizzle 32/64/128B == row size).
+// * B (weights, fp16 [tap][cout][cin]) is fetched by TMA the same way.
+// * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (single thread), warps 2-5 = epilogue
+//   (tcgen05.ld TMEM -> regs -> bias/act/residual -> global).  Accumulators are double-buffered in TMEM so the
+//   epilogue of tile i overlaps the MMAs of tile i+1.  Persistent CTAs, one per SM, static tile striding.
+//
+// Replaces: ultralytics Conv/C2f/Bottleneck/Detect convs (3P) and TrackNet Conv2DBlock
+// (/root/reference/trackers/ball_tracker/models.py:5-17) with BN folded into weight/bias.
+#include <cstring>
+#include <mutex>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace pb {
+
+struct ConvSmemTail {
+  uint64_t full[kConvMaxStages];
+  uint64_t empty[kConvMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == PB_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == PB_ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
+  if (act == PB_ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-v));
+  return v;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+               const __grid_constant__ ConvKParams kp) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024B alignment is required by the 128B swizzle pattern; align explicitly (the launch adds 1 KB of slack).
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t stage_bytes = kp.a_bytes + kp.b_bytes;
+  ConvSmemTail* tail = reinterpret_cast<ConvSmemTail*>(smem + (size_t)kp.stages * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int k_iters = kp.taps * kp.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kp.stages; ++i) {
+      mbar_init(&tail->full[i], 1);
+      mbar_init(&tail->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tail->tmem_full[i], 1);
+      mbar_init(&tail->tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tail->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int TW = 1 << kp.tw_log2, TH = 1 << kp.th_log2;
+      const int TN = 128 >> (kp.tw_log2 + kp.th_log2);
+      for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int nt = t % kp.n_ntiles;
+        t /= kp.n_ntiles;
+        const int tw = t % kp.tiles_w;
+        t /= kp.tiles_w;
+        const int th = t % kp.tiles_h;
+        const int tn = t / kp.tiles_h;
+        for (int tap = 0; tap < kp.taps; ++tap) {
+          const int cw = tw * TW + kp.tap_dw[tap];
+          const int ch = th * TH + kp.tap_dh[tap];
+          const int cc = kp.c_in_off + kp.tap_dc[tap];
+          for (int kb = 0; kb < kp.kblocks; ++kb) {
+            mbar_wait(&tail->empty[stage], phase ^ 1);
+            uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+            uint8_t* b_dst = a_dst + kp.a_bytes;
+            mbar_arrive_expect_tx(&tail->full[stage], kp.a_bytes + kp.b_tx_bytes);
+            tma_load_5d(a_dst, &tmap_a, &tail->full[stage], cc + kb * kp.KB, cw, kp.tap_d2[tap], ch, tn * TN);
+            tma_load_3d(b_dst, &tmap_w, &tail->full[stage], kb * kp.KB, nt * kp.BN, tap);
+            if (++stage == kp.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== UMMA issuer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t swz = (uint32_t)kp.KB * 2u;
+      const int ksteps = kp.KB / 16;
+      for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&tail->full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = a_addr + kp.a_bytes;
+          const uint64_t adesc = umma_desc_kmajor(a_addr, swz);
+          const uint64_t bdesc = umma_desc_kmajor(b_addr, swz);
+#pragma unroll 4
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 K-elements = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kp.idesc,
+                     (uint32_t)((it | k) != 0));
+          }
+          umma_commit(&tail->empty[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == kp.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tail->tmem_full[acc]);  // accumulator ready for the epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue (4 warps, one TMEM lane quarter each) ==============================
+    const int quarter = warp & 3;
+    const int p = quarter * 32 + lane;  // row of the M=128 tile handled by this thread
+    const int TWm = (1 << kp.tw_log2) - 1, THm = (1 << kp.th_log2) - 1;
+    const int tw_i = p & TWm;
+    const int th_i = (p >> kp.tw_log2) & THm;
+    const int tn_i = p >> (kp.tw_log2 + kp.th_log2);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int nt = t % kp.n_ntiles;
+      t /= kp.n_ntiles;
+      const int tw = t % kp.tiles_w;
+      t /= kp.tiles_w;
+      const int th = t % kp.tiles_h;
+      const int tn = t / kp.tiles_h;
+      const int ow = (tw << kp.tw_log2) + tw_i;
+      const int oh = (th << kp.th_log2) + th_i;
+      const int n = tn * (128 >> (kp.tw_log2 + kp.th_log2)) + tn_i;
+      const bool valid = (ow < kp.Wo) && (oh < kp.Ho) && (n < kp.N);
+      const size_t pix = ((size_t)n * kp.Ho + oh) * kp.Wo + ow;
+
+      mbar_wait(&tail->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u;
+      for (int c = 0; c < kp.BN; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_addr + (uint32_t)c, r);
+        tmem_ld_wait();
+        const int ch0 = nt * kp.BN + c;  // first output channel of this chunk
+        if (valid && ch0 < kp.cout_store) {
+          float v[16];
+          const float4* b4 = reinterpret_cast<const float4*>(kp.bias + ch0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = __ldg(b4 + q);
+            v[4 * q + 0] = apply_act(__uint_as_float(r[4 * q + 0]) + b.x, kp.act);
+            v[4 * q + 1] = apply_act(__uint_as_float(r[4 * q + 1]) + b.y, kp.act);
+            v[4 * q + 2] = apply_act(__uint_as_float(r[4 * q + 2]) + b.z, kp.act);
+            v[4 * q + 3] = apply_act(__uint_as_float(r[4 * q + 3]) + b.w, kp.act);
+          }
+          if (kp.res != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(kp.res + pix * kp.res_C + kp.res_coff + ch0);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint4 rv = __ldg(rp + g);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h2[j]);
+                v[8 * g + 2 * j] += f.x;
+                v[8 * g + 2 * j + 1] += f.y;
+              }
+            }
+          }
+          if (kp.out_mode == PB_OUT_F16_NHWC || kp.out_mode == PB_OUT_F16_NHWC_UP2) {
+            uint4 pk[2];
+            __half2* h2 = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h2[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            __half* ob = reinterpret_cast<__half*>(kp.out);
+            const int ngrp = (kp.cout_store - ch0 >= 16) ? 2 : 1;  // cout_store is a multiple of 8
+            if (kp.out_mode == PB_OUT_F16_NHWC) {
+              uint4* op = reinterpret_cast<uint4*>(ob + pix * kp.out_C + kp.out_coff + ch0);
+              op[0] = pk[0];
+              if (ngrp == 2) op[1] = pk[1];
+            } else {
+              const int Wo2 = kp.Wo * 2;
+#pragma unroll
+              for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                  const size_t pix2 = ((size_t)n * (kp.Ho * 2) + (oh * 2 + dy)) * Wo2 + (ow * 2 + dx);
+                  uint4* op = reinterpret_cast<uint4*>(ob + pix2 * kp.out_C + kp.out_coff + ch0);
+                  op[0] = pk[0];
+                  if (ngrp == 2) op[1] = pk[1];
+                }
+            }
+          } else if (kp.out_mode == PB_OUT_F32_NHWC) {
+            float* op = reinterpret_cast<float*>(kp.out) + pix * kp.out_C + kp.out_coff + ch0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (ch0 + j < kp.cout_store) op[j] = v[j];
+          } else {  // PB_OUT_F32_NCHW
+            float* ob = reinterpret_cast<float*>(kp.out);
+            const size_t plane = (size_t)kp.Ho * kp.Wo;
+            const size_t base = (size_t)n * kp.cout_store * plane + (size_t)oh * kp.Wo + ow;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (ch0 + j < kp.cout_store) ob[base + (size_t)(ch0 + j) * plane] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
+  PB_CHECK(d && plan, "conv: null argument");
+  PB_CHECK(d->ksize == 1 || d->ksize == 3, "conv: ksize %d unsupported", d->ksize);
+  PB_CHECK(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
+  PB_CHECK(!(d->stride == 2 && d->ksize == 1), "conv: 1x1 stride-2 unsupported");
+  PB_CHECK(d->cin > 0 && d->cin % 16 == 0, "conv: cin %d must be a positive multiple of 16", d->cin);
+  PB_CHECK(d->cout_pad > 0 && d->cout_pad % 16 == 0, "conv: cout_pad %d must be a multiple of 16", d->cout_pad);
+  PB_CHECK(d->C % 8 == 0 && d->c_in_off >= 0 && d->c_in_off + d->cin <= d->C, "conv: bad input channel slice");
+  PB_CHECK(d->c_in_off % 8 == 0, "conv: c_in_off must be a multiple of 8");
+  PB_CHECK((reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+           "conv: pointers must be 16-byte aligned");
+  PB_CHECK(d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0), "conv: stride 2 needs even H and W");
+  PB_CHECK(d->cout_store > 0 && d->cout_store <= d->cout_pad, "conv: bad cout_store");
+  const bool f16out = d->out_mode == PB_OUT_F16_NHWC || d->out_mode == PB_OUT_F16_NHWC_UP2;
+  if (f16out) {
+    PB_CHECK(d->cout_store % 8 == 0 && d->out_coff % 8 == 0 && d->out_C % 8 == 0,
+             "conv: f16 output needs cout_store/out_coff/out_C multiples of 8");
+    PB_CHECK(d->out_coff + d->cout_store <= d->out_C, "conv: output slice exceeds out_C");
+  }
+  if (d->res) {
+    PB_CHECK(d->res_C % 8 == 0 && d->res_coff % 8 == 0 && (reinterpret_cast<uintptr_t>(d->res) & 15) == 0,
+             "conv: residual must be 16-byte aligned slices");
+    PB_CHECK(d->cout_store % 16 == 0 || true, "unreachable");
+  }
+  EncodeTiledFn encode = get_encode_fn();
+  PB_CHECK(encode != nullptr, "conv: cuTensorMapEncodeTiled not available (no CUDA driver?)");
+
+  plan->desc = *d;
+  ConvKParams& kp = plan->kp;
+  memset(&kp, 0, sizeof(kp));
+  const int s = d->stride;
+  kp.N = d->N;
+  kp.Ho = d->H / s;
+  kp.Wo = d->W / s;
+  kp.taps = d->ksize * d->ksize;
+  kp.KB = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0 ? 32 : 16);
+  kp.kblocks = d->cin / kp.KB;
+  // N tile: largest multiple-of-16 divisor of cout_pad that is <= 256
+  int nn = (d->cout_pad + 255) / 256;
+  while (d->cout_pad % nn != 0 || (d->cout_pad / nn) % 16 != 0) ++nn;
+  kp.n_ntiles = nn;
+  kp.BN = d->cout_pad / nn;
+  PB_CHECK(kp.BN >= 16 && kp.BN <= 256, "conv: cannot tile cout_pad %d", d->cout_pad);
+
+  // pixel tile shape (TN x TH x TW = 128): minimise the number of tiles, prefer wide tiles
+  long best_cost = -1;
+  int best_tw = 0, best_th = 0;
+  for (int twl = 7; twl >= 2; --twl) {
+    for (int thl = 7 - twl; thl >= 0; --thl) {
+      const int TW = 1 << twl, TH = 1 << thl, TN = 128 >> (twl + thl);
+      const long cost = (long)((kp.Wo + TW - 1) / TW) * ((kp.Ho + TH - 1) / TH) * ((kp.N + TN - 1) / TN);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_tw = twl;
+        best_th = thl;
+      }
+    }
+  }
+  kp.tw_log2 = best_tw;
+  kp.th_log2 = best_th;
+  const int TW = 1 << best_tw, TH = 1 << best_th, TN = 128 >> (best_tw + best_th);
+  kp.tiles_w = (kp.Wo + TW - 1) / TW;
+  kp.tiles_h = (kp.Ho + TH - 1) / TH;
+  kp.tiles_n = (kp.N + TN - 1) / TN;
+  kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n * kp.n_ntiles;
+  (void)ilog2;
+
+  kp.c_in_off = d->c_in_off;
+  for (int r = 0; r < d->ksize; ++r)
+    for (int q = 0; q < d->ksize; ++q) {
+      const int t = r * d->ksize + q;
+      const int dy = r - d->ksize / 2, dx = q - d->ksize / 2;  // input offset relative to s*o
+      if (s == 1) {
+        kp.tap_dc[t] = 0;
+        kp.tap_dw[t] = dx;
+        kp.tap_d2[t] = 0;
+        kp.tap_dh[t] = dy;
+      } else {
+        // input col = 2*ow + dx  ->  (w/2 coord, parity): dx=-1 -> (ow-1, 1); 0 -> (ow, 0); 1 -> (ow, 1)
+        kp.tap_dw[t] = (dx < 0) ? -1 : 0;
+        kp.tap_dc[t] = (dx != 0) ? d->C : 0;
+        kp.tap_dh[t] = (dy < 0) ? -1 : 0;
+        kp.tap_d2[t] = (dy != 0) ? 1 : 0;
+      }
+    }
+  kp.bias = d->bias;
+  kp.act = d->act;
+  kp.res = reinterpret_cast<const __half*>(d->res);
+  kp.res_C = d->res_C;
+  kp.res_coff = d->res_coff;
+  kp.out = d->out;
+  kp.out_C = d->out_C;
+  kp.out_coff = d->out_coff;
+  kp.out_mode = d->out_mode;
+  kp.cout_store = d->cout_store;
+  kp.idesc = umma_idesc_f16(kp.BN, 0);
+  kp.a_bytes = 128u * kp.KB * 2u;
+  kp.b_tx_bytes = (uint32_t)kp.BN * kp.KB * 2u;
+  kp.b_bytes = (kp.b_tx_bytes + 1023u) & ~1023u;
+  const uint32_t stage_bytes = kp.a_bytes + kp.b_bytes;
+  const size_t budget = 200 * 1024;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > kConvMaxStages) stages = kConvMaxStages;
+  PB_CHECK(stages >= 2, "conv: stage too large (%u bytes)", stage_bytes);
+  kp.stages = stages;
+  plan->smem_bytes = (size_t)stages * stage_bytes + sizeof(ConvSmemTail) + 1024;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // force 1 CTA/SM (TMEM: 512 cols each)
+  plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+
+  const CUtensorMapSwizzle swz = kp.KB == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : kp.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                               : CU_TENSOR_MAP_SWIZZLE_32B;
+  {
+    // activations: stride 1 -> (C, W, 1, H, N); stride 2 -> (2C, W/2, 2, H/2, N)
+    const cuuint64_t C = (cuuint64_t)d->C, W = (cuuint64_t)d->W, H = (cuuint64_t)d->H;
+    cuuint64_t dims[5];
+    cuuint64_t strides[4];
+    if (s == 1) {
+      dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)d->N;
+      strides[0] = C * 2; strides[1] = W * C * 2; strides[2] = W * C * 2; strides[3] = H * W * C * 2;
+    } else {
+      dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = (cuuint64_t)d->N;
+      strides[0] = 2 * C * 2; strides[1] = W * C * 2; strides[2] = 2 * W * C * 2; strides[3] = H * W * C * 2;
+    }
+    cuuint32_t box[5] = {(cuuint32_t)kp.KB, (cuuint32_t)TW, 1, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&plan->tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d->in), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(A) failed with %d (N=%d H=%d W=%d C=%d s=%d)", (int)r,
+             d->N, d->H, d->W, d->C, s);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)d->cout_pad, (cuuint64_t)kp.taps};
+    cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * d->cout_pad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kp.KB, (cuuint32_t)kp.BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&plan->tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d->weight), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+  }
+  return 0;
+}
+
+int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  PB_CHECK(attr_err == cudaSuccess, "conv: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
+  conv_tc_kernel<<<plan->grid, kConvThreads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->kp);
+  PB_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CUDA-core reference kernel (tests only): same descriptor, one thread per (pixel, out-channel)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void conv_reference_kernel(pb_conv_desc d, int Ho, int Wo) {
+  const long total = (long)d.N * Ho * Wo * d.cout_pad;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % d.cout_pad);
+    long pixl = idx / d.cout_pad;
+    const int ow = (int)(pixl % Wo);
+    const int oh = (int)((pixl / Wo) % Ho);
+    const int n = (int)(pixl / ((long)Wo * Ho));
+    if (co >= d.cout_store) continue;
+    const __half* in = reinterpret_cast<const __half*>(d.in);
+    const __half* w = reinterpret_cast<const __half*>(d.weight);
+    float acc = 0.f;
+    const int pad = d.ksize / 2;
+    for (int r = 0; r < d.ksize; ++r)
+      for (int q = 0; q < d.ksize; ++q) {
+        const int ih = oh * d.stride + r - pad, iw = ow * d.stride + q - pad;
+        if (ih < 0 || ih >= d.H || iw < 0 || iw >= d.W) continue;
+        const __half* ip = in + (((size_t)n * d.H + ih) * d.W + iw) * d.C + d.c_in_off;
+        const __half* wp = w + ((size_t)(r * d.ksize + q) * d.cout_pad + co) * d.cin;
+        for (int c = 0; c < d.cin; ++c) acc += __half2float(ip[c]) * __half2float(wp[c]);
+      }
+    float v = acc + d.bias[co];
+    if (d.act == PB_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (d.act == PB_ACT_SILU) v = v / (1.f + expf(-v));
+    else if (d.act == PB_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+    const size_t pix = ((size_t)n * Ho + oh) * Wo + ow;
+    if (d.res) v += __half2float(reinterpret_cast<const __half*>(d.res)[pix * d.res_C + d.res_coff + co]);
+    if (d.out_mode == PB_OUT_F16_NHWC) {
+      reinterpret_cast<__half*>(d.out)[pix * d.out_C + d.out_coff + co] = __float2half_rn(v);
+    } else if (d.out_mode == PB_OUT_F16_NHWC_UP2) {
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t pix2 = ((size_t)n * (Ho * 2) + (oh * 2 + dy)) * (Wo * 2) + (ow * 2 + dx);
+          reinterpret_cast<__half*>(d.out)[pix2 * d.out_C + d.out_coff + co] = __float2half_rn(v);
+        }
+    } else if (d.out_mode == PB_OUT_F32_NHWC) {
+      reinterpret_cast<float*>(d.out)[pix * d.out_C + d.out_coff + co] = v;
+    } else {
+      reinterpret_cast<float*>(d.out)[(((size_t)n * d.cout_store + co) * Ho + oh) * Wo + ow] = v;
+    }
+  }
+}
+
+int conv_reference_launch(const pb_conv_desc* d, cudaStream_t stream) {
+  PB_CHECK(d != nullptr, "conv_reference: null desc");
+  const int Ho = d->H / d->stride, Wo = d->W / d->stride;
+  const long total = (long)d->N * Ho * Wo * d->cout_pad;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  conv_reference_kernel<<<blocks, 256, 0, stream>>>(*d, Ho, Wo);
+  PB_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace pb

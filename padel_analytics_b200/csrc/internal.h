@@ -1,0 +1,79 @@
+// Internal helpers shared by the translation units of libpadel_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/padel_b200.h"
+
+namespace pb {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int num_sms();
+
+#define PB_CHECK(cond, ...)         \
+  do {                              \
+    if (!(cond)) {                  \
+      pb::set_error(__VA_ARGS__);   \
+      return 1;                     \
+    }                               \
+  } while (0)
+
+#define PB_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      pb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 1;                                                                                \
+    }                                                                                          \
+  } while (0)
+
+// ---- conv plan (built once per layer; holds TMA descriptors + launch geometry) -------------------------------
+constexpr int kConvMaxStages = 12;
+constexpr int kConvThreads = 192;  // warp0: TMA producer, warp1: UMMA issuer, warps 2-5: epilogue
+
+struct ConvKParams {
+  int N, Ho, Wo;
+  int tiles_w, tiles_h, tiles_n, n_ntiles, total_tiles;
+  int tw_log2, th_log2;  // TW*TH*TN == 128
+  int taps, kblocks, KB, BN, stages;
+  int c_in_off;
+  int tap_dc[9], tap_dw[9], tap_d2[9], tap_dh[9];
+  const float* bias;
+  int act;
+  const __half* res;
+  int res_C, res_coff;
+  void* out;
+  int out_C, out_coff, out_mode, cout_store;
+  uint32_t idesc;
+  uint32_t a_bytes, b_bytes, b_tx_bytes;
+};
+
+struct ConvPlan {
+  pb_conv_desc desc;
+  ConvKParams kp;
+  CUtensorMap tmap_a;
+  CUtensorMap tmap_w;
+  int grid;
+  size_t smem_bytes;
+};
+
+int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan);
+int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
+int conv_reference_launch(const pb_conv_desc* d, cudaStream_t stream);
+
+// aux kernels (aux_kernels.cu)
+int launch_maxpool2(const void* in, int N, int H, int W, int C, int c_off, int c, void* out, int out_C,
+                    int out_coff, cudaStream_t s);
+int launch_upsample2(const void* in, int N, int H, int W, int C, int c_off, int c, void* out, int out_C,
+                     int out_coff, cudaStream_t s);
+int launch_sppf_pool(void* buf, int N, int H, int W, int C, int c, cudaStream_t s);
+
+}  // namespace pb

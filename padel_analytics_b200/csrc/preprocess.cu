@@ -1,0 +1,219 @@
+// Frame pre-processing on device, bit-exact with the CPU libraries the reference pipeline calls:
+//   * OpenCV 8-bit INTER_LINEAR resize + 114 border  (ultralytics LetterBox [3P], used by
+//     /root/reference/trackers/players_tracker/players_tracker.py:351-359)
+//   * Pillow BICUBIC(antialias) two-pass fixed-point resample
+//     (players_keypoints_tracker.py:260-266, keypoints_tracker.py:190-194, ball_tracker/iterable.py:188)
+//   * u8 -> fp16 NHWC packing (ToTensor /255; TrackNet window assembly iterable.py:167-199)
+// All coefficient tables come from the host (engine/resample.py); kernels do integer arithmetic only.
+#include "internal.h"
+
+namespace pb {
+
+__device__ __forceinline__ uint4 pack_px16_first(float a, float b, float c) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+  h[0] = __floats2half2_rn(a, b);
+  h[1] = __floats2half2_rn(c, 0.f);
+  h[2] = __floats2half2_rn(0.f, 0.f);
+  h[3] = h[2];
+  return v;
+}
+
+__global__ void letterbox_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws, __half* __restrict__ dst,
+                                 int Hn, int Wn, int rh, int rw, int top, int left, const int* __restrict__ xofs,
+                                 const int* __restrict__ xcoef, const int* __restrict__ yofs,
+                                 const int* __restrict__ ycoef, int c0, int c1, int c2) {
+  const long total = (long)B * Hn * Wn;
+  const bool identity = (rh == Hs && rw == Ws);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wn);
+    const int y = (int)((i / Wn) % Hn);
+    const int b = (int)(i / ((long)Wn * Hn));
+    int px[3] = {114, 114, 114};
+    const int ry = y - top, rx = x - left;
+    if (ry >= 0 && ry < rh && rx >= 0 && rx < rw) {
+      const uint8_t* img = src + (size_t)b * Hs * Ws * 3;
+      if (identity) {
+        const uint8_t* p = img + ((size_t)ry * Ws + rx) * 3;
+        px[0] = p[0]; px[1] = p[1]; px[2] = p[2];
+      } else {
+        const int sx = xofs[rx], sy = yofs[ry];
+        const int sx1 = min(sx + 1, Ws - 1), sy1 = min(sy + 1, Hs - 1);
+        const int a0 = xcoef[2 * rx], a1 = xcoef[2 * rx + 1];
+        const int b0 = ycoef[2 * ry], b1 = ycoef[2 * ry + 1];
+        const uint8_t* p00 = img + ((size_t)sy * Ws + sx) * 3;
+        const uint8_t* p01 = img + ((size_t)sy * Ws + sx1) * 3;
+        const uint8_t* p10 = img + ((size_t)sy1 * Ws + sx) * 3;
+        const uint8_t* p11 = img + ((size_t)sy1 * Ws + sx1) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int r0 = p00[c] * a0 + p01[c] * a1;  // horizontal pass, 11 fractional bits
+          const int r1 = p10[c] * a0 + p11[c] * a1;
+          // cv::VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>> (scalar form)
+          px[c] = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+        }
+      }
+    }
+    const float inv = 1.f / 255.f;
+    uint4* o = reinterpret_cast<uint4*>(dst + (size_t)i * 16);
+    o[0] = pack_px16_first(px[c0] * inv, px[c1] * inv, px[c2] * inv);
+    o[1] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// Pillow ImagingResampleHorizontal_8bpc / Vertical_8bpc: ss = 1<<21; ss += px*k; out = clip8(ss >> 22)
+__global__ void pil_horizontal_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws,
+                                      uint8_t* __restrict__ tmp, int Wo, const int* __restrict__ bounds,
+                                      const int* __restrict__ kk, int ksize, int swap_rb) {
+  const long total = (long)B * Hs * Wo;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int xo = (int)(i % Wo);
+    const long row = i / Wo;  // b*Hs + y
+    const int xmin = bounds[2 * xo], xs = bounds[2 * xo + 1];
+    const int* k = kk + (size_t)xo * ksize;
+    const uint8_t* p = src + ((size_t)row * Ws + xmin) * 3;
+    int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+    for (int x = 0; x < xs; ++x) {
+      const int kv = k[x];
+      s0 += p[3 * x + 0] * kv;
+      s1 += p[3 * x + 1] * kv;
+      s2 += p[3 * x + 2] * kv;
+    }
+    uint8_t* o = tmp + (size_t)i * 3;
+    const uint8_t v0 = (uint8_t)min(max(s0 >> 22, 0), 255);
+    const uint8_t v1 = (uint8_t)min(max(s1 >> 22, 0), 255);
+    const uint8_t v2 = (uint8_t)min(max(s2 >> 22, 0), 255);
+    o[0] = swap_rb ? v2 : v0;
+    o[1] = v1;
+    o[2] = swap_rb ? v0 : v2;
+  }
+}
+
+__global__ void pil_vertical_kernel(const uint8_t* __restrict__ tmp, int B, int Hs, int Wo,
+                                    uint8_t* __restrict__ dst, int Ho, const int* __restrict__ bounds,
+                                    const int* __restrict__ kk, int ksize) {
+  const long total = (long)B * Ho * Wo * 3;
+  const int rowlen = Wo * 3;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int xc = (int)(i % rowlen);
+    const int yo = (int)((i / rowlen) % Ho);
+    const int b = (int)(i / ((long)rowlen * Ho));
+    const int ymin = bounds[2 * yo], ys = bounds[2 * yo + 1];
+    const int* k = kk + (size_t)yo * ksize;
+    const uint8_t* p = tmp + ((size_t)b * Hs + ymin) * rowlen + xc;
+    int s = 1 << 21;
+    for (int y = 0; y < ys; ++y) s += p[(size_t)y * rowlen] * k[y];
+    dst[i] = (uint8_t)min(max(s >> 22, 0), 255);
+  }
+}
+
+__global__ void u8_to_f16_nhwc16_kernel(const uint8_t* __restrict__ src, long npix, __half* __restrict__ dst, int c0,
+                                        int c1, int c2) {
+  const float inv = 1.f / 255.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
+    const uint8_t* p = src + i * 3;
+    uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
+    o[0] = pack_px16_first(p[c0] * inv, p[c1] * inv, p[c2] * inv);
+    o[1] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// x[b, h, w, :] = [median(3), frame[first+b+0](3), ..., frame[first+b+7](3), 0*5] / 255   (32 channels, fp16)
+__global__ void tracknet_pack_kernel(const uint8_t* __restrict__ frames, int ring, int first_slot,
+                                     const uint8_t* __restrict__ median, int B, int HW, __half* __restrict__ x) {
+  const long total = (long)B * HW * 4;  // 4 groups of 8 channels per pixel
+  const float inv = 1.f / 255.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 3);
+    const long pixl = i >> 2;
+    const int pix = (int)(pixl % HW);
+    const int b = (int)(pixl / HW);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;  // logical channel 0..31
+      float val = 0.f;
+      if (ch < 3) {
+        val = median[(size_t)pix * 3 + ch] * inv;
+      } else if (ch < 27) {
+        const int f = (ch - 3) / 3, c = (ch - 3) % 3;
+        const int slot = (first_slot + b + f) % ring;
+        val = frames[((size_t)slot * HW + pix) * 3 + c] * inv;
+      }
+      v[j] = val;
+    }
+    uint4 pk;
+    __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(x + (size_t)pixl * 32 + g * 8) = pk;
+  }
+}
+
+static int grid_for(long total, int threads) {
+  long b = (total + threads - 1) / threads;
+  const long cap = (long)num_sms() * 32;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" {
+
+int pb_letterbox_u8_f16(const uint8_t* src, int B, int Hs, int Ws, void* dst, int Hn, int Wn, int rh, int rw,
+                        int top, int left, const int32_t* xofs, const int32_t* xcoef, const int32_t* yofs,
+                        const int32_t* ycoef, int c0, int c1, int c2, void* stream) {
+  PB_CHECK(src && dst, "letterbox: null pointer");
+  PB_CHECK((rh == Hs && rw == Ws) || (xofs && xcoef && yofs && ycoef), "letterbox: missing tables");
+  PB_CHECK(top >= 0 && left >= 0 && top + rh <= Hn && left + rw <= Wn, "letterbox: bad geometry");
+  const long total = (long)B * Hn * Wn;
+  letterbox_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, B, Hs, Ws, reinterpret_cast<__half*>(dst), Hn, Wn, rh, rw, top, left, xofs, xcoef, yofs, ycoef, c0, c1,
+      c2);
+  PB_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int pb_pil_resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* tmp, uint8_t* dst, int Ho, int Wo,
+                     const int32_t* bounds_h, const int32_t* kk_h, int ksize_h, const int32_t* bounds_v,
+                     const int32_t* kk_v, int ksize_v, int swap_rb, void* stream) {
+  PB_CHECK(src && tmp && dst && bounds_h && kk_h && bounds_v && kk_v, "pil_resize: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long t1 = (long)B * Hs * Wo;
+  pil_horizontal_kernel<<<grid_for(t1, 256), 256, 0, s>>>(src, B, Hs, Ws, tmp, Wo, bounds_h, kk_h, ksize_h, swap_rb);
+  PB_CUDA(cudaGetLastError());
+  const long t2 = (long)B * Ho * Wo * 3;
+  pil_vertical_kernel<<<grid_for(t2, 256), 256, 0, s>>>(tmp, B, Hs, Wo, dst, Ho, bounds_v, kk_v, ksize_v);
+  PB_CUDA(cudaGetLastError());
+  count_launch(2);
+  return 0;
+}
+
+int pb_u8_to_f16_nhwc16(const uint8_t* src, int B, int H, int W, void* dst, int c0, int c1, int c2, void* stream) {
+  PB_CHECK(src && dst, "u8_to_f16: null pointer");
+  const long npix = (long)B * H * W;
+  u8_to_f16_nhwc16_kernel<<<grid_for(npix, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, npix, reinterpret_cast<__half*>(dst), c0, c1, c2);
+  PB_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int pb_tracknet_pack_windows(const uint8_t* frames, int ring, int first_slot, const uint8_t* median, int B, int H,
+                             int W, void* x, void* stream) {
+  PB_CHECK(frames && median && x, "tracknet_pack: null pointer");
+  PB_CHECK(ring >= 8, "tracknet_pack: ring must hold at least 8 frames");
+  const long total = (long)B * H * W * 4;
+  tracknet_pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, ring, first_slot, median, B, H * W, reinterpret_cast<__half*>(x));
+  PB_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // extern "C"

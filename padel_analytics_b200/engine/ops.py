@@ -1,0 +1,115 @@
+"""Host-side helpers over the C ABI: weight packing, conv descriptors, NHWC buffers."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+
+
+def pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+def fold_bn(w: torch.Tensor, gamma, beta, mean, var, eps: float):
+    """Conv(no bias)+BatchNorm -> (w', b').  Same algebra as ultralytics fuse_conv_and_bn (3P) applied by
+    model.fuse(); TrackNet's Conv2DBlock (/root/reference/trackers/ball_tracker/models.py:5-17) has the same form."""
+    scale = gamma / torch.sqrt(var + eps)
+    return w * scale.reshape(-1, 1, 1, 1), beta - mean * scale
+
+
+def pack_conv_weight(w: torch.Tensor, b: torch.Tensor | None, cin_pad: int, cout_pad: int, device,
+                     cin_map: list[int] | None = None):
+    """(Cout,Cin,k,k) fp32 -> half [k*k][cout_pad][cin_pad] + float bias [cout_pad] (zero padded).
+
+    cin_map[i] = position of logical input channel i in the padded input tensor (for concat slices that are
+    individually padded); default identity."""
+    cout, cin, kh, kw = w.shape
+    assert kh == kw
+    wp = torch.zeros(kh * kw, cout_pad, cin_pad, dtype=torch.float32)
+    src = w.detach().float().permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    if cin_map is None:
+        wp[:, :cout, :cin] = src
+    else:
+        idx = torch.as_tensor(cin_map, dtype=torch.long)
+        wp[:, :cout, idx] = src
+    bp = torch.zeros(cout_pad, dtype=torch.float32)
+    if b is not None:
+        bp[:cout] = b.detach().float()
+    return wp.to(torch.float16).contiguous().to(device), bp.contiguous().to(device)
+
+
+def make_conv_desc(x: torch.Tensor, c_in_off: int, cin: int, w: torch.Tensor, b: torch.Tensor, ksize: int,
+                   stride: int, act: int, out: torch.Tensor, out_coff: int, out_mode: int = L.OUT_F16_NHWC,
+                   cout_store: int | None = None, res: torch.Tensor | None = None, res_coff: int = 0) -> L.ConvDesc:
+    """x: NHWC half tensor (N,H,W,C). w: packed half [taps][cout_pad][cin]. out: NHWC tensor (half or float), or
+    (N,C,H,W) float for OUT_F32_NCHW."""
+    N, H, W, Ct = x.shape
+    cout_pad = w.shape[1]
+    assert w.shape[2] == cin and w.shape[0] == ksize * ksize
+    d = L.ConvDesc()
+    d.in_ = x.data_ptr()
+    d.N, d.H, d.W, d.C = N, H, W, Ct
+    d.c_in_off, d.cin = c_in_off, cin
+    d.weight, d.bias = w.data_ptr(), b.data_ptr()
+    d.cout_pad, d.ksize, d.stride, d.act = cout_pad, ksize, stride, act
+    if res is not None:
+        d.res, d.res_C, d.res_coff = res.data_ptr(), res.shape[-1], res_coff
+    else:
+        d.res, d.res_C, d.res_coff = None, 0, 0
+    d.out = out.data_ptr()
+    d.out_C = out.shape[-1] if out_mode != L.OUT_F32_NCHW else out.shape[1]
+    d.out_coff, d.out_mode = out_coff, out_mode
+    d.cout_store = cout_pad if cout_store is None else cout_store
+    return d
+
+
+def conv2d(desc: L.ConvDesc, reference: bool = False) -> None:
+    fn = L.lib().pb_conv2d_reference if reference else L.lib().pb_conv2d
+    L.check(fn(C.byref(desc), L.stream_ptr()))
+
+
+class Program:
+    """Ordered list of device ops bound to fixed buffers (pb_program)."""
+
+    def __init__(self):
+        self._h = L.lib().pb_program_create()
+        self._keep = []  # tensors referenced by raw pointer
+
+    def __del__(self):
+        try:
+            if self._h:
+                L.lib().pb_program_destroy(self._h)
+        except Exception:
+            pass
+
+    def keep(self, *tensors):
+        self._keep.extend(tensors)
+
+    def conv(self, desc: L.ConvDesc):
+        L.check(L.lib().pb_program_add_conv(self._h, C.byref(desc)))
+
+    def maxpool2(self, x, c_off, c, out, out_coff):
+        N, H, W, Ct = x.shape
+        L.check(L.lib().pb_program_add_maxpool2(self._h, x.data_ptr(), N, H, W, Ct, c_off, c, out.data_ptr(),
+                                                out.shape[-1], out_coff))
+
+    def upsample2(self, x, c_off, c, out, out_coff):
+        N, H, W, Ct = x.shape
+        L.check(L.lib().pb_program_add_upsample2(self._h, x.data_ptr(), N, H, W, Ct, c_off, c, out.data_ptr(),
+                                                 out.shape[-1], out_coff))
+
+    def sppf_pool(self, buf, c):
+        N, H, W, Ct = buf.shape
+        L.check(L.lib().pb_program_add_sppf_pool(self._h, buf.data_ptr(), N, H, W, Ct, c))
+
+    @property
+    def num_ops(self) -> int:
+        return L.lib().pb_program_num_ops(self._h)
+
+    def run(self, first: int | None = None, last: int | None = None):
+        if first is None:
+            L.check(L.lib().pb_program_run(self._h, L.stream_ptr()))
+        else:
+            L.check(L.lib().pb_program_run_range(self._h, first, last, L.stream_ptr()))

@@ -1,0 +1,107 @@
+"""tcgen05 implicit-GEMM conv vs torch fp32 conv2d on the same fp16-rounded operands (and vs the CUDA-core
+reference kernel).  Tolerance: fp16 output rounding (rel 2^-10) + fp32 accumulation-order noise."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from padel_analytics_b200 import _lib as L
+from padel_analytics_b200.engine import ops
+
+pytestmark = pytest.mark.gpu
+
+ACT = {L.ACT_NONE: lambda v: v, L.ACT_RELU: torch.relu, L.ACT_SILU: F.silu, L.ACT_SIGMOID: torch.sigmoid}
+
+
+def run_case(N, H, W, cin, cout, k, s, act, cin_real=None, c_total=None, c_in_off=0, out_mode=L.OUT_F16_NHWC,
+             residual=False, out_coff=0, out_extra=0, seed=0, reference=False):
+    g = torch.Generator().manual_seed(seed)
+    dev = "cuda"
+    cin_real = cin_real or cin
+    c_total = c_total or cin
+    x = torch.zeros(N, H, W, c_total)
+    x[..., c_in_off:c_in_off + cin_real] = torch.randn(N, H, W, cin_real, generator=g)
+    x16 = x.half()
+    w = torch.randn(cout, cin_real, k, k, generator=g) / (cin_real * k * k) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    cout_pad = ops.pad16(cout)
+    wp, bp = ops.pack_conv_weight(w, b, cin, cout_pad, dev)
+    xd = x16.to(dev)
+    Ho, Wo = H // s, W // s
+    up = 2 if out_mode == L.OUT_F16_NHWC_UP2 else 1
+    if out_mode in (L.OUT_F16_NHWC, L.OUT_F16_NHWC_UP2):
+        cs = cout_pad
+        out = torch.full((N, Ho * up, Wo * up, cout_pad + out_coff + out_extra), 7.0, dtype=torch.float16, device=dev)
+    elif out_mode == L.OUT_F32_NHWC:
+        cs = cout
+        out = torch.full((N, Ho, Wo, cout + out_coff + out_extra), 7.0, dtype=torch.float32, device=dev)
+    else:
+        cs = cout
+        out = torch.full((N, cout, Ho, Wo), 7.0, dtype=torch.float32, device=dev)
+    res = None
+    if residual:
+        res = torch.randn(N, Ho, Wo, cout_pad, generator=g).half().to(dev)
+    d = ops.make_conv_desc(xd, c_in_off, cin, wp, bp, k, s, act, out, out_coff, out_mode, cs, res, 0)
+    ops.conv2d(d, reference=reference)
+    torch.cuda.synchronize()
+    # fp32 reference on the fp16-rounded operands
+    xr = x16[..., c_in_off:c_in_off + cin_real].float().permute(0, 3, 1, 2)
+    wr = w.half().float()
+    y = F.conv2d(xr, wr, b, stride=s, padding=k // 2)
+    y = ACT[act](y)
+    if residual:
+        y = y + res.cpu().float()[..., :cout].permute(0, 3, 1, 2)
+    o = out.cpu().float()
+    if out_mode == L.OUT_F32_NCHW:
+        got = o
+    else:
+        if up == 2:
+            y = F.interpolate(y, scale_factor=2, mode="nearest")
+        got = o[..., out_coff:out_coff + cout].permute(0, 3, 1, 2)
+        # untouched neighbours keep the fill value
+        if out_coff:
+            assert torch.all(o[..., :out_coff] == 7.0)
+        if out_extra:
+            assert torch.all(o[..., out_coff + cs:] == 7.0)
+    err = (got - y).abs()
+    tol = 2e-3 + 2e-3 * y.abs()
+    bad = (err > tol).float().mean().item()
+    return bad, err.max().item()
+
+
+CASES = [
+    # N, H, W, cin, cout, k, s, act, kwargs
+    dict(N=1, H=16, W=128, cin=64, cout=64, k=1, s=1, act=L.ACT_NONE),
+    dict(N=1, H=16, W=128, cin=64, cout=64, k=3, s=1, act=L.ACT_RELU),
+    dict(N=2, H=36, W=64, cin=128, cout=256, k=3, s=1, act=L.ACT_RELU),
+    dict(N=1, H=36, W=64, cin=256, cout=512, k=3, s=1, act=L.ACT_RELU),
+    dict(N=2, H=24, W=40, cin=32, cout=32, k=3, s=1, act=L.ACT_SILU),
+    dict(N=2, H=24, W=40, cin=16, cout=16, k=3, s=1, act=L.ACT_SILU),
+    dict(N=2, H=24, W=40, cin=48, cout=80, k=3, s=1, act=L.ACT_SILU),
+    dict(N=2, H=48, W=80, cin=16, cout=32, k=3, s=2, act=L.ACT_SILU),
+    dict(N=2, H=48, W=80, cin=64, cout=128, k=3, s=2, act=L.ACT_SILU),
+    dict(N=3, H=12, W=20, cin=256, cout=256, k=3, s=1, act=L.ACT_SILU),
+    dict(N=4, H=6, W=10, cin=128, cout=64, k=1, s=1, act=L.ACT_SILU),
+    dict(N=2, H=24, W=40, cin=32, cout=32, k=3, s=1, act=L.ACT_SILU, residual=True),
+    dict(N=2, H=24, W=40, cin=32, cout=32, k=3, s=1, act=L.ACT_SILU, c_total=96, c_in_off=32, out_coff=64,
+         out_extra=32),
+    dict(N=2, H=16, W=32, cin=32, cout=27, k=1, s=1, act=L.ACT_NONE, cin_real=27, out_mode=L.OUT_F32_NHWC,
+         out_coff=64, out_extra=3),
+    dict(N=2, H=16, W=32, cin=64, cout=8, k=1, s=1, act=L.ACT_SIGMOID, out_mode=L.OUT_F32_NCHW),
+    dict(N=2, H=16, W=32, cin=64, cout=64, k=3, s=1, act=L.ACT_RELU, out_mode=L.OUT_F16_NHWC_UP2),
+    dict(N=1, H=72, W=128, cin=768, cout=256, k=3, s=1, act=L.ACT_RELU),
+    dict(N=1, H=288, W=512, cin=32, cout=64, k=3, s=1, act=L.ACT_RELU, cin_real=27),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_reference_kernel_matches_torch(case):
+    if case["H"] * case["W"] * case["cin"] * case["cout"] > 2e9:
+        pytest.skip("too slow for the CUDA-core kernel")
+    bad, mx = run_case(**case, reference=True)
+    assert bad == 0.0, f"reference kernel: {bad*100:.3f}% elements out of tolerance (max err {mx})"
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_tcgen05_conv_matches_torch(case):
+    bad, mx = run_case(**case)
+    assert bad == 0.0, f"tcgen05 kernel: {bad*100:.3f}% elements out of tolerance (max err {mx})"
