@@ -1,0 +1,394 @@
+"""YOLOv8 detect / pose inference on the B200 kernels behind the `ultralytics.YOLO(...).predict()` surface the
+reference trackers use:
+    /root/reference/trackers/players_tracker/players_tracker.py:303,338-339,351-359
+    /root/reference/trackers/players_keypoints_tracker/players_keypoints_tracker.py:238,285-292
+    /root/reference/trackers/keypoints_tracker/keypoints_tracker.py:169,238-245
+Graph = ultralytics yolov8{,-pose}.yaml layers 0..22 (third-party), executed as a static list of
+fused conv kernels over preallocated NHWC fp16 buffers; concat / chunk / residual / upsample are channel-slice
+reads and writes (no copies except the two nearest-upsamples and SPPF pooling).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from . import ops, resample
+
+
+# ---- result containers with the attribute surface the trackers (and sv.Detections.from_ultralytics) touch ----------
+@dataclass
+class Boxes:
+    data: torch.Tensor  # (N,6) xyxy, conf, cls  (CPU float32)
+
+    @property
+    def xyxy(self):
+        return self.data[:, :4]
+
+    @property
+    def conf(self):
+        return self.data[:, 4]
+
+    @property
+    def cls(self):
+        return self.data[:, 5]
+
+    @property
+    def id(self):
+        return None
+
+    def __len__(self):
+        return self.data.shape[0]
+
+
+@dataclass
+class Keypoints:
+    data: torch.Tensor  # (N,K,D)
+
+    @property
+    def xy(self):
+        return self.data[..., :2]
+
+    @property
+    def conf(self):
+        return self.data[..., 2] if self.data.shape[-1] == 3 else None
+
+
+@dataclass
+class Result:
+    boxes: Boxes
+    keypoints: Keypoints | None
+    names: dict
+    orig_shape: tuple
+
+
+def _fold(sd, p, eps=1e-3):
+    return ops.fold_bn(sd[f"{p}.conv.weight"].float(), sd[f"{p}.bn.weight"].float(), sd[f"{p}.bn.bias"].float(),
+                       sd[f"{p}.bn.running_mean"].float(), sd[f"{p}.bn.running_var"].float(), eps)
+
+
+class YoloEngine:
+    """Drop-in for `ultralytics.YOLO(model_path)`: .predict(source, conf=, iou=, imgsz=, device=, classes=, max_det=),
+    .to(device), .names.  `ckpt` is a dict {'model': state_dict (ultralytics key names), 'nc', 'kpt_shape'} or a path
+    to a torch file holding one."""
+
+    CAND_CAP = 4096  # candidates per image kept for NMS (ultralytics max_nms is 30000; overflow raises)
+
+    def __init__(self, ckpt, max_batch: int = 8, device: str = "cuda"):
+        if not torch.cuda.is_available():
+            raise L.PbError("YoloEngine needs a CUDA device (no CPU fallback)")
+        L.lib()
+        if not isinstance(ckpt, dict):
+            ckpt = torch.load(ckpt, map_location="cpu", weights_only=False)
+        self.sd = {k: v for k, v in ckpt["model"].items()}
+        self.nc = int(ckpt["nc"])
+        self.kpt_shape = tuple(ckpt["kpt_shape"]) if ckpt.get("kpt_shape") else None
+        self.nk = self.kpt_shape[0] * self.kpt_shape[1] if self.kpt_shape else 0
+        self.names = ckpt.get("names") or {i: ("person" if (i == 0 and self.nc == 80) else f"class{i}")
+                                           for i in range(self.nc)}
+        self.device = torch.device(device)
+        self.B = max_batch
+        self._progs = {}  # (Hn, Wn) -> built program state
+        self._packed = {}
+        self._tables = {}
+        self._stage = None
+
+    def to(self, device):
+        return self
+
+    # ------------------------------------------------------------------------------------------------------
+    # weights
+    # ------------------------------------------------------------------------------------------------------
+    def _wb(self, prefix, cin_pad, cout_pad, bn=True):
+        key = (prefix, cin_pad, cout_pad)
+        if key not in self._packed:
+            if bn:
+                w, b = _fold(self.sd, prefix)
+            else:
+                w, b = self.sd[f"{prefix}.weight"].float(), self.sd[f"{prefix}.bias"].float()
+            self._packed[key] = ops.pack_conv_weight(w, b, cin_pad, cout_pad, self.device)
+        return self._packed[key]
+
+    def _cout(self, prefix, bn=True):
+        return self.sd[f"{prefix}.conv.weight" if bn else f"{prefix}.weight"].shape[0]
+
+    # ------------------------------------------------------------------------------------------------------
+    # program construction for one network input size
+    # ------------------------------------------------------------------------------------------------------
+    def _build(self, Hn, Wn):
+        B, dev, sd = self.B, self.device, self.sd
+        P = ops.Program()
+        bufs = []
+
+        def buf(h, w, c, dtype=torch.float16):
+            t = torch.zeros((B, h, w, c), dtype=dtype, device=dev)
+            bufs.append(t)
+            return t
+
+        SILU = L.ACT_SILU
+
+        def conv(x, coff, cin, prefix, out, ooff, k, s, res=None, res_off=0):
+            cout = self._cout(prefix)
+            w, b = self._wb(prefix, cin, ops.pad16(cout))
+            P.conv(ops.make_conv_desc(x, coff, cin, w, b, k, s, SILU, out, ooff, L.OUT_F16_NHWC, None, res, res_off))
+            return ops.pad16(cout)
+
+        def c2f(x, coff, cin, i, out, ooff, shortcut):
+            """ultralytics C2f (App. A.2): cv1 -> [y0,y1] ; y_{j+2} = Bottleneck_j(y_{j+1}) ; cv2(cat(y))."""
+            pre = f"model.{i}"
+            c = self._cout(f"{pre}.cv1") // 2
+            n = 0
+            while f"{pre}.m.{n}.cv1.conv.weight" in sd:
+                n += 1
+            _, h, w_, _ = x.shape
+            cat = buf(h, w_, (2 + n) * c)
+            tmp = buf(h, w_, c)
+            conv(x, coff, cin, f"{pre}.cv1", cat, 0, 1, 1)
+            for j in range(n):
+                conv(cat, (1 + j) * c, c, f"{pre}.m.{j}.cv1", tmp, 0, 3, 1)
+                conv(tmp, 0, c, f"{pre}.m.{j}.cv2", cat, (2 + j) * c, 3, 1, res=cat if shortcut else None,
+                     res_off=(1 + j) * c)
+            conv(cat, 0, (2 + n) * c, f"{pre}.cv2", out, ooff, 1, 1)
+
+        c0, c1, c2, c3, c4 = (self._cout(f"model.{i}") for i in (0, 1, 3, 5, 7))
+        for c in (c0, c1, c2, c3, c4):
+            if c % 16:
+                raise L.PbError(f"YoloEngine: channel width {c} is not a multiple of 16")
+        H2, W2, H4, W4, H8, W8 = Hn // 2, Wn // 2, Hn // 4, Wn // 4, Hn // 8, Wn // 8
+        H16, W16, H32, W32 = Hn // 16, Wn // 16, Hn // 32, Wn // 32
+        x0 = buf(Hn, Wn, 16)
+        b0, b1, b2 = buf(H2, W2, c0), buf(H4, W4, c1), buf(H4, W4, c1)
+        b3 = buf(H8, W8, c2)
+        cat14 = buf(H8, W8, c3 + c2)  # [up(12) c3 | P3 c2]
+        b5 = buf(H16, W16, c3)
+        cat11 = buf(H16, W16, c4 + c3)  # [up(9) c4 | P4 c3]
+        b7, b8 = buf(H32, W32, c4), buf(H32, W32, c4)
+        sp = buf(H32, W32, 4 * (c4 // 2))
+        cat20 = buf(H32, W32, c3 + c4)  # [conv19 c3 | P5 c4]
+        cat17 = buf(H16, W16, c2 + c3)  # [conv16 c2 | h4 c3]
+        o3, o4, o5 = buf(H8, W8, c2), buf(H16, W16, c3), buf(H32, W32, c4)
+
+        conv(x0, 0, 16, "model.0", b0, 0, 3, 2)
+        conv(b0, 0, c0, "model.1", b1, 0, 3, 2)
+        c2f(b1, 0, c1, 2, b2, 0, True)
+        conv(b2, 0, c1, "model.3", b3, 0, 3, 2)
+        c2f(b3, 0, c2, 4, cat14, c3, True)  # P3
+        conv(cat14, c3, c2, "model.5", b5, 0, 3, 2)
+        c2f(b5, 0, c3, 6, cat11, c4, True)  # P4
+        conv(cat11, c4, c3, "model.7", b7, 0, 3, 2)
+        c2f(b7, 0, c4, 8, b8, 0, True)
+        conv(b8, 0, c4, "model.9.cv1", sp, 0, 1, 1)  # SPPF
+        P.sppf_pool(sp, c4 // 2)
+        conv(sp, 0, 4 * (c4 // 2), "model.9.cv2", cat20, c3, 1, 1)  # P5
+        P.upsample2(cat20, c3, c4, cat11, 0)  # layers 10-11
+        c2f(cat11, 0, c4 + c3, 12, cat17, c2, False)  # h4
+        P.upsample2(cat17, c2, c3, cat14, 0)  # layers 13-14
+        c2f(cat14, 0, c3 + c2, 15, o3, 0, False)
+        conv(o3, 0, c2, "model.16", cat17, 0, 3, 2)
+        c2f(cat17, 0, c2 + c3, 18, o4, 0, False)
+        conv(o4, 0, c3, "model.19", cat20, 0, 3, 2)
+        c2f(cat20, 0, c3 + c4, 21, o5, 0, False)
+
+        # heads: per level box / cls (/ kpt) branches -> one fp32 NHWC map (B,h,w,64+nc+nk)
+        fC = 64 + self.nc + self.nk
+        feats, levels = [], []
+        branches = [("cv2", 64, 0), ("cv3", self.nc, 64)]
+        if self.nk:
+            branches.append(("cv4", self.nk, 64 + self.nc))
+        for l, (f, cf, st) in enumerate(((o3, c2, 8), (o4, c3, 16), (o5, c4, 32))):
+            _, h, w_, _ = f.shape
+            feat = buf(h, w_, fC, torch.float32)
+            for name, cout_real, off in branches:
+                pre = f"model.22.{name}.{l}"
+                cm = ops.pad16(self._cout(f"{pre}.0"))
+                t1, t2 = buf(h, w_, cm), buf(h, w_, cm)
+                conv(f, 0, cf, f"{pre}.0", t1, 0, 3, 1)
+                conv(t1, 0, cm, f"{pre}.1", t2, 0, 3, 1)
+                w, b = self._wb(f"{pre}.2", cm, ops.pad16(cout_real), bn=False)
+                P.conv(ops.make_conv_desc(t2, 0, cm, w, b, 1, 1, L.ACT_NONE, feat, off, L.OUT_F32_NHWC, cout_real))
+            feats.append(feat)
+            levels.append((feat, h, w_, st))
+        lv = (L.YoloLevel * 3)()
+        for l, (feat, h, w_, st) in enumerate(levels):
+            lv[l].feat, lv[l].h, lv[l].w, lv[l].stride = feat.data_ptr(), h, w_, st
+        rowlen = 6 + self.nk
+        st = dict(prog=P, bufs=bufs, x0=x0, levels=lv, fC=fC, rowlen=rowlen, Hn=Hn, Wn=Wn,
+                  cand=torch.zeros((B, self.CAND_CAP, rowlen), dtype=torch.float32, device=dev),
+                  cand_anchor=torch.zeros((B, self.CAND_CAP), dtype=torch.int32, device=dev),
+                  cand_count=torch.zeros((B,), dtype=torch.int32, device=dev),
+                  feats=feats)
+        return st
+
+    def _state(self, Hn, Wn):
+        key = (Hn, Wn)
+        if key not in self._progs:
+            if Hn % 32 or Wn % 32:
+                raise L.PbError(f"YoloEngine: network input {Hn}x{Wn} must be a multiple of 32")
+            self._progs[key] = self._build(Hn, Wn)
+        return self._progs[key]
+
+    # ------------------------------------------------------------------------------------------------------
+    # pre-processing front ends (all write st['x0'])
+    # ------------------------------------------------------------------------------------------------------
+    def _upload(self, frames) -> torch.Tensor:
+        """list of HWC u8 arrays / (n,H,W,3) tensor (host or device) -> device u8 (n,H,W,3)."""
+        if isinstance(frames, torch.Tensor):
+            t = frames
+        else:
+            t = torch.from_numpy(np.stack([np.ascontiguousarray(f) for f in frames]))
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[-1] != 3:
+            raise L.PbError("frames must be uint8 (n,H,W,3)")
+        if t.shape[0] > self.B:
+            raise L.PbError(f"batch {t.shape[0]} exceeds engine max_batch {self.B}")
+        if t.device != self.device:
+            n = t.shape[0]
+            if self._stage is None or self._stage.shape[1:] != t.shape[1:]:
+                self._stage = torch.empty((self.B,) + tuple(t.shape[1:]), dtype=torch.uint8, device=self.device)
+            self._stage[:n].copy_(t, non_blocking=True)
+            t = self._stage[:n]
+        return t.contiguous()
+
+    def _letterbox(self, frames_dev, imgsz, chan_map):
+        n, Hs, Ws, _ = frames_dev.shape
+        g = resample.letterbox_geometry(Hs, Ws, imgsz, 32, auto=True)
+        st = self._state(g["Hn"], g["Wn"])
+        key = ("lb", Hs, Ws, g["rh"], g["rw"])
+        if key not in self._tables:
+            xo, xc = resample.cv2_linear_tables(Ws, g["rw"])
+            yo, yc = resample.cv2_linear_tables(Hs, g["rh"])
+            self._tables[key] = tuple(torch.from_numpy(np.ascontiguousarray(a)).to(self.device) for a in (xo, xc, yo, yc))
+        xo, xc, yo, yc = self._tables[key]
+        L.check(L.lib().pb_letterbox_u8_f16(frames_dev.data_ptr(), n, Hs, Ws, st["x0"].data_ptr(), g["Hn"], g["Wn"],
+                                            g["rh"], g["rw"], g["top"], g["left"], xo.data_ptr(), xc.data_ptr(),
+                                            yo.data_ptr(), yc.data_ptr(), chan_map[0], chan_map[1], chan_map[2],
+                                            L.stream_ptr()))
+        return st, (Hs, Ws)
+
+    def _pil_square(self, frames_dev, size):
+        """BGR frames -> RGB -> Pillow-exact bicubic resize to size x size -> network input (RGB order)."""
+        n, Hs, Ws, _ = frames_dev.shape
+        st = self._state(size, size)
+        key = ("pil", Hs, Ws, size)
+        if key not in self._tables:
+            bh, kh, ksh = resample.pil_bicubic_tables(Ws, size)
+            bv, kv, ksv = resample.pil_bicubic_tables(Hs, size)
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+            self._tables[key] = dict(bh=up(bh), kh=up(kh), ksh=ksh, bv=up(bv), kv=up(kv), ksv=ksv,
+                                     tmp=torch.empty((self.B, Hs, size, 3), dtype=torch.uint8, device=self.device),
+                                     dst=torch.empty((self.B, size, size, 3), dtype=torch.uint8, device=self.device))
+        t = self._tables[key]
+        L.check(L.lib().pb_pil_resize_u8(frames_dev.data_ptr(), n, Hs, Ws, t["tmp"].data_ptr(), t["dst"].data_ptr(),
+                                         size, size, t["bh"].data_ptr(), t["kh"].data_ptr(), t["ksh"],
+                                         t["bv"].data_ptr(), t["kv"].data_ptr(), t["ksv"], 1, L.stream_ptr()))
+        L.check(L.lib().pb_u8_to_f16_nhwc16(t["dst"].data_ptr(), n, size, size, st["x0"].data_ptr(), 0, 1, 2,
+                                            L.stream_ptr()))
+        return st, (size, size)
+
+    # ------------------------------------------------------------------------------------------------------
+    # forward + decode + NMS + host epilogue
+    # ------------------------------------------------------------------------------------------------------
+    def _detect(self, st, n, conf, iou, classes, max_det):
+        lib = L.lib()
+        st["prog"].run()
+        if classes is not None and len(classes) != 1:
+            raise L.PbError("YoloEngine: only a single-class filter (or None) is supported")
+        cf = -1 if classes is None else int(classes[0])
+        kdim = self.kpt_shape[1] if self.kpt_shape else 0
+        L.check(lib.pb_yolo_decode(st["levels"], 3, self.B, st["fC"], self.nc, self.nk, kdim, float(conf), cf,
+                                   st["cand"].data_ptr(), st["cand_anchor"].data_ptr(), st["cand_count"].data_ptr(),
+                                   self.CAND_CAP, L.stream_ptr()))
+        key = ("out", max_det)
+        if key not in st:
+            st[key] = (torch.zeros((self.B, max_det, st["rowlen"]), dtype=torch.float32, device=self.device),
+                       torch.zeros((self.B,), dtype=torch.int32, device=self.device),
+                       torch.zeros((self.B, max_det, st["rowlen"]), dtype=torch.float32).pin_memory(),
+                       torch.zeros((2, self.B), dtype=torch.int32).pin_memory())
+        out, cnt, out_h, cnt_h = st[key]
+        L.check(lib.pb_yolo_nms(st["cand"].data_ptr(), st["cand_anchor"].data_ptr(), st["cand_count"].data_ptr(),
+                                self.B, self.CAND_CAP, st["rowlen"], float(iou), max_det, out.data_ptr(),
+                                cnt.data_ptr(), L.stream_ptr()))
+        out_h.copy_(out, non_blocking=True)
+        cnt_h[0].copy_(cnt, non_blocking=True)
+        cnt_h[1].copy_(st["cand_count"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if int(cnt_h[1][:n].max()) > self.CAND_CAP:
+            raise L.PbError(f"YoloEngine: {int(cnt_h[1][:n].max())} candidates exceed CAND_CAP={self.CAND_CAP}")
+        return out_h.numpy(), cnt_h[0].numpy()
+
+    def _results(self, rows, counts, n, net_hw, orig_hw):
+        """scale_boxes / scale_coords / clip / keypoint conf<0.5 -> 0 (ultralytics ops, SURVEY App. A.4 vi-vii),
+        float32 arithmetic on the host (a few dozen numbers per image)."""
+        h1, w1 = net_hw
+        h0, w0 = orig_hw
+        gain = min(h1 / h0, w1 / w0)
+        padb = (round((w1 - w0 * gain) / 2 - 0.1), round((h1 - h0 * gain) / 2 - 0.1))
+        padk = ((w1 - w0 * gain) / 2, (h1 - h0 * gain) / 2)
+        g32 = np.float32(gain)
+        res = []
+        for i in range(n):
+            r = rows[i, : counts[i]].astype(np.float32, copy=True)
+            box = r[:, :6].copy()
+            box[:, [0, 2]] -= np.float32(padb[0])
+            box[:, [1, 3]] -= np.float32(padb[1])
+            box[:, :4] /= g32
+            box[:, [0, 2]] = np.clip(box[:, [0, 2]], 0, w0)
+            box[:, [1, 3]] = np.clip(box[:, [1, 3]], 0, h0)
+            kp = None
+            if self.kpt_shape:
+                K, D = self.kpt_shape
+                k = r[:, 6:].reshape(-1, K, D).copy()
+                k[..., 0] -= np.float32(padk[0])
+                k[..., 1] -= np.float32(padk[1])
+                k[..., 0] /= g32
+                k[..., 1] /= g32
+                k[..., 0] = np.clip(k[..., 0], 0, w0)
+                k[..., 1] = np.clip(k[..., 1], 0, h0)
+                if D == 3:
+                    m = k[..., 2] < 0.5
+                    k[..., 0][m] = 0
+                    k[..., 1][m] = 0
+                kp = Keypoints(torch.from_numpy(k))
+            res.append(Result(Boxes(torch.from_numpy(box)), kp, self.names, (h0, w0)))
+        return res
+
+    @torch.no_grad()
+    def predict(self, source, conf=0.25, iou=0.7, imgsz=640, device=None, classes=None, max_det=300, **kw):
+        """ultralytics-compatible entry: `source` is a list of BGR ndarrays or of PIL RGB images (one batch)."""
+        if len(source) == 0:
+            return []
+        if isinstance(source[0], np.ndarray):
+            arrs, cmap = source, (2, 1, 0)  # BGR in -> network sees RGB (App. A.4 i,iii)
+        else:
+            arrs, cmap = [np.asarray(im) for im in source], (0, 1, 2)  # PIL RGB -> BGR -> flipped back
+        if len({a.shape for a in arrs}) != 1:
+            raise L.PbError("YoloEngine.predict: all images of a batch must share one shape")
+        out = []
+        for i in range(0, len(arrs), self.B):
+            chunk = arrs[i:i + self.B]
+            fr = self._upload(chunk)
+            st, orig = self._letterbox(fr, imgsz, cmap)
+            rows, counts = self._detect(st, len(chunk), conf, iou, classes, max_det)
+            out += self._results(rows, counts, len(chunk), (st["Hn"], st["Wn"]), orig)
+        return out
+
+    @torch.no_grad()
+    def predict_frames(self, frames, prep: str, conf, iou, imgsz, classes=None, max_det=300):
+        """Fused fast path used by this repo's trackers: raw BGR video frames in, all pre-processing on device.
+        prep='letterbox_q1': PlayerTracker path (processor BGR->RGB + ultralytics' own flip => the network sees the
+            frame's B,G,R in its R,G,B slots) + LetterBox.
+        prep='pil_square' : PlayerKeypoints/Keypoints path (BGR->RGB, PIL resize to imgsz x imgsz).
+        Returned coordinates are in the pre-processed image's pixel space, exactly like model.predict() on the
+        processed sample (full frame for letterbox_q1, imgsz x imgsz for pil_square)."""
+        fr = self._upload(frames)
+        n = fr.shape[0]
+        if prep == "letterbox_q1":
+            st, orig = self._letterbox(fr, imgsz, (0, 1, 2))
+        elif prep == "pil_square":
+            st, orig = self._pil_square(fr, imgsz)
+        else:
+            raise L.PbError(f"unknown prep {prep!r}")
+        rows, counts = self._detect(st, n, conf, iou, classes, max_det)
+        return self._results(rows, counts, n, (st["Hn"], st["Wn"]), orig)

@@ -1,0 +1,160 @@
+"""PlayerKeypointsTracker on the B200 engine — API of
+/root/reference/trackers/players_keypoints_tracker/players_keypoints_tracker.py (:15-327)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Iterable, Optional, Type
+
+import numpy as np
+
+from ..engine.yolo_engine import YoloEngine
+from .tracker import NoPredictFrames, Object, Tracker
+
+
+@dataclass
+class PlayerKeypoint:
+    id: int
+    name: str
+    xy: tuple[float, float]
+
+    def asint(self):
+        return tuple(int(v) for v in self.xy)
+
+    @classmethod
+    def from_json(cls, x: dict):
+        return cls(**x)
+
+    def serialize(self) -> dict:
+        return {"id": self.id, "name": self.name, "xy": self.xy}
+
+    def draw(self, frame):
+        import cv2
+
+        cv2.circle(frame, self.asint(), radius=2, color=(255, 0, 0), thickness=-1)
+        return frame
+
+
+class PlayerKeypoints:
+    KEYPOINTS_NAMES = ["left_foot", "right_foot", "torso", "right_shoulder", "left_shoulder", "head", "neck",
+                       "left_hand", "right_hand", "right_knee", "left_knee", "right_elbow", "left_elbow"]
+    CONNECTIONS = [("left_foot", "left_knee"), ("left_knee", "torso"), ("right_foot", "right_knee"),
+                   ("right_knee", "torso"), ("torso", "left_shoulder"), ("torso", "right_shoulder"),
+                   ("left_hand", "left_elbow"), ("left_elbow", "left_shoulder"), ("left_shoulder", "neck"),
+                   ("neck", "head"), ("right_hand", "right_elbow"), ("right_elbow", "right_shoulder"),
+                   ("right_shoulder", "neck")]
+
+    def __init__(self, player_keypoints: list[PlayerKeypoint]):
+        self.player_keypoints = player_keypoints
+        self.keypoints_by_name = {k.name: k for k in player_keypoints}
+
+    @classmethod
+    def from_json(cls, x: dict):
+        return cls([PlayerKeypoint.from_json(k) for k in x["player_keypoints"]])
+
+    def serialize(self) -> dict:
+        return {"player_keypoints": [k.serialize() for k in self.player_keypoints]}
+
+    def __len__(self):
+        return len(self.player_keypoints)
+
+    def __iter__(self):
+        return iter(self.player_keypoints)
+
+    def __getitem__(self, name: str) -> PlayerKeypoint:
+        assert name in self.KEYPOINTS_NAMES
+        return self.keypoints_by_name[name]
+
+    def draw(self, frame):
+        import cv2
+
+        pts = {k.name: k.asint() for k in self.player_keypoints}
+        if not pts:
+            return frame
+        for a, b in self.CONNECTIONS:
+            cv2.line(frame, pts[a], pts[b], color=(255, 0, 0), thickness=2)
+        return frame
+
+
+class PlayersKeypoints(Object):
+    def __init__(self, players_keypoints: list[PlayerKeypoints]) -> None:
+        super().__init__()
+        self.players_keypoints = players_keypoints
+
+    @classmethod
+    def from_json(cls, x) -> "PlayersKeypoints":
+        return cls([PlayerKeypoints.from_json(p) for p in x])
+
+    def serialize(self) -> list[dict]:
+        return [p.serialize() for p in self.players_keypoints]
+
+    def __len__(self):
+        return len(self.players_keypoints)
+
+    def __iter__(self):
+        return iter(self.players_keypoints)
+
+    def __getitem__(self, i):
+        return self.players_keypoints[i]
+
+    def draw(self, frame):
+        for p in self.players_keypoints:
+            frame = p.draw(frame)
+        return frame
+
+
+class PlayerKeypointsTracker(Tracker):
+    CONF = 0.25
+    IOU = 0.7
+
+    def __init__(self, model_path, train_image_size: int, batch_size: int, load_path: Optional[str | Path] = None,
+                 save_path: Optional[str | Path] = None):
+        super().__init__(load_path=load_path, save_path=save_path)
+        self.model = YoloEngine(model_path, max_batch=batch_size)  # reference: YOLO(model_path) (:238)
+        assert train_image_size in (640, 1280)
+        self.train_image_size = train_image_size
+        self.batch_size = batch_size
+
+    def video_info_post_init(self, video_info) -> "PlayerKeypointsTracker":
+        return self
+
+    def object(self) -> Type[Object]:
+        return PlayersKeypoints
+
+    def draw_kwargs(self) -> dict:
+        return {}
+
+    def __str__(self) -> str:
+        return "players_keypoints_tracker"
+
+    def restart(self) -> None:
+        self.results.restart()
+
+    def to(self, device: str) -> None:
+        self.model.to(device)
+
+    def detect_sample(self, sample):
+        return self.model.predict_frames(sample, "pil_square", conf=self.CONF, iou=self.IOU,
+                                         imgsz=self.train_image_size, classes=[0])
+
+    def postprocess(self, results, frame_hw) -> list[PlayersKeypoints]:
+        """players_keypoints_tracker.py:276-318.  The reference's `.squeeze(0)` / `len()==2` juggling crashes for
+        exactly one or two detected players; here every detection count is handled uniformly."""
+        ratio_x = frame_hw[1] / self.train_image_size
+        ratio_y = frame_hw[0] / self.train_image_size
+        out = []
+        for result in results:
+            players = []
+            for det in result.keypoints.xy:  # (K,2) per player
+                players.append(PlayerKeypoints([
+                    PlayerKeypoint(id=i, name=PlayerKeypoints.KEYPOINTS_NAMES[i],
+                                   xy=(kp[0].item() * ratio_x, kp[1].item() * ratio_y))
+                    for i, kp in enumerate(det)]))
+            out.append(PlayersKeypoints(players))
+        return out
+
+    def predict_sample(self, sample: Iterable[np.ndarray], **kwargs) -> list[PlayersKeypoints]:
+        return self.postprocess(self.detect_sample(sample), sample[0].shape[:2])
+
+    def predict_frames(self, frame_generator, **kwargs):
+        raise NoPredictFrames()

@@ -1,0 +1,199 @@
+"""Device kernels vs the CPU libraries / oracle on identical inputs: integer paths must be bit-exact."""
+import ctypes as C
+
+import cv2
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from padel_analytics_b200 import _lib as L
+from padel_analytics_b200.engine import resample
+from oracle import tracknet as OT
+from oracle import yolov8 as OY
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _frames(n, h=1080, w=1920, seed=0):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (n, h // 8, w // 8, 3), dtype=np.uint8)
+    up = np.stack([cv2.resize(b, (w, h), interpolation=cv2.INTER_CUBIC) for b in base])
+    noise = rng.integers(-20, 21, up.shape, dtype=np.int16)
+    return np.clip(up.astype(np.int16) + noise, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("hw", [(1080, 1920), (2160, 3840), (720, 1280)])
+def test_letterbox_bit_exact(hw):
+    fr = _frames(2, *hw)
+    g = resample.letterbox_geometry(hw[0], hw[1], 640)
+    xo, xc = resample.cv2_linear_tables(hw[1], g["rw"])
+    yo, yc = resample.cv2_linear_tables(hw[0], g["rh"])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    src, xo, xc, yo, yc = t(fr), t(xo), t(xc), t(yo), t(yc)
+    dst = torch.zeros((2, g["Hn"], g["Wn"], 16), dtype=torch.float16, device=DEV)
+    L.check(L.lib().pb_letterbox_u8_f16(src.data_ptr(), 2, hw[0], hw[1], dst.data_ptr(), g["Hn"], g["Wn"], g["rh"],
+                                        g["rw"], g["top"], g["left"], xo.data_ptr(), xc.data_ptr(), yo.data_ptr(),
+                                        yc.data_ptr(), 2, 1, 0, L.stream_ptr()))
+    torch.cuda.synchronize()
+    for i in range(2):
+        ref = OY.letterbox(fr[i], 640, auto=True)[..., ::-1]  # BGR -> RGB like the predict pipeline
+        exp = (torch.from_numpy(np.ascontiguousarray(ref)).float() * np.float32(1.0 / 255.0)).half()
+        got = dst[i, ..., :3].cpu()
+        assert got.shape == exp.shape
+        assert torch.equal(got, exp), f"max diff {(got.float()-exp.float()).abs().max()*255:.3f} levels"
+        assert torch.all(dst[i, ..., 3:] == 0)
+
+
+@pytest.mark.parametrize("size", [(512, 288), (1280, 1280), (640, 640)])
+@pytest.mark.parametrize("hw", [(1080, 1920), (2160, 3840)])
+def test_pil_resize_bit_exact(size, hw):
+    fr = _frames(2, *hw, seed=1)
+    Wo, Ho = size
+    bh, kh, ksh = resample.pil_bicubic_tables(hw[1], Wo)
+    bv, kv, ksv = resample.pil_bicubic_tables(hw[0], Ho)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    src, bh, kh, bv, kv = t(fr), t(bh), t(kh), t(bv), t(kv)
+    tmp = torch.zeros((2, hw[0], Wo, 3), dtype=torch.uint8, device=DEV)
+    dst = torch.zeros((2, Ho, Wo, 3), dtype=torch.uint8, device=DEV)
+    L.check(L.lib().pb_pil_resize_u8(src.data_ptr(), 2, hw[0], hw[1], tmp.data_ptr(), dst.data_ptr(), Ho, Wo,
+                                     bh.data_ptr(), kh.data_ptr(), ksh, bv.data_ptr(), kv.data_ptr(), ksv, 1,
+                                     L.stream_ptr()))
+    torch.cuda.synchronize()
+    for i in range(2):
+        ref = np.array(Image.fromarray(cv2.cvtColor(fr[i], cv2.COLOR_BGR2RGB)).resize((Wo, Ho)))
+        got = dst[i].cpu().numpy()
+        assert np.array_equal(got, ref), f"max diff {np.abs(got.astype(int)-ref).max()}"
+
+
+def test_tracknet_pack_windows():
+    rng = np.random.default_rng(2)
+    ring, B, H, W = 12, 4, 32, 64
+    frames = rng.integers(0, 256, (ring, H, W, 3), dtype=np.uint8)
+    med = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    x = torch.zeros((B, H, W, 32), dtype=torch.float16, device=DEV)
+    first = 7
+    L.check(L.lib().pb_tracknet_pack_windows(torch.from_numpy(frames).to(DEV).data_ptr(), ring, first,
+                                             torch.from_numpy(med).to(DEV).data_ptr(), B, H, W, x.data_ptr(),
+                                             L.stream_ptr()))
+    torch.cuda.synchronize()
+    got = x.cpu().float()
+    for b in range(B):
+        chans = [med] + [frames[(first + b + f) % ring] for f in range(8)]
+        exp = np.concatenate(chans, -1).astype(np.float64) / 255.0  # iterable.py:186-197
+        assert np.abs(got[b, ..., :27].numpy() - exp).max() < 6e-4
+        assert torch.all(got[b, ..., 27:] == 0)
+
+
+@pytest.mark.parametrize("T,bs", [(30, 8), (8, 4), (9, 8), (15, 3), (23, 16)])
+def test_ensemble_matches_reference_loop(T, bs):
+    H, W = 24, 40
+    g = torch.Generator().manual_seed(T)
+    S = T - 7
+    preds = torch.rand((S, 8, H, W), generator=g)
+    exp = OT.ensemble_reference_loop(preds, T, bs)
+    buf = torch.zeros((7 + bs, 8, H, W), device=DEV)
+    got = []
+    w0 = 0
+    while w0 < S:
+        nb = min(bs, S - w0)
+        buf[7:7 + nb] = preds[w0:w0 + nb].to(DEV)
+        nfr = nb + (7 if w0 + nb == S else 0)
+        mask = torch.zeros((nfr, H, W), dtype=torch.uint8, device=DEV)
+        ens = torch.zeros((nfr, H, W), device=DEV)
+        L.check(L.lib().pb_tracknet_ensemble(buf.data_ptr(), 7 + nb, w0 - 7, S, w0, nfr, H, W, 0.5, mask.data_ptr(),
+                                             ens.data_ptr(), L.stream_ptr()))
+        torch.cuda.synchronize()
+        got.append(ens.cpu())
+        assert torch.equal(mask.cpu().bool(), ens.cpu() > 0.5)
+        buf[:7] = buf[nb:nb + 7].clone()
+        w0 += nb
+    got = torch.cat(got)
+    assert got.shape == exp.shape
+    assert torch.equal(got, exp), f"max diff {(got-exp).abs().max().item():.3e}"
+
+
+def _blob_mask(rng, H, W, nblobs):
+    m = np.zeros((H, W), np.uint8)
+    for _ in range(nblobs):
+        cy, cx = rng.integers(0, H), rng.integers(0, W)
+        ry, rx = rng.integers(1, 6), rng.integers(1, 9)
+        yy, xx = np.ogrid[:H, :W]
+        m |= (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1).astype(np.uint8)
+    return m
+
+
+def test_ccl_bbox_matches_cv2():
+    rng = np.random.default_rng(3)
+    H, W = 288, 512
+    masks = [np.zeros((H, W), np.uint8)]
+    masks += [_blob_mask(rng, H, W, n) for n in (1, 2, 3, 5, 8, 13, 40, 120)]
+    masks += [(rng.random((H, W)) < d).astype(np.uint8) for d in (0.001, 0.01, 0.1, 0.3, 0.5, 0.7)]
+    m = np.ones((H, W), np.uint8); masks.append(m)  # everything foreground
+    m = np.zeros((H, W), np.uint8); m[0, 0] = 1; m[H - 1, W - 1] = 1; masks.append(m)  # equal areas -> tie rule
+    m = np.zeros((H, W), np.uint8); m[10:20, 10:20] = 1; m[12:18, 12:18] = 0; m[14:16, 14:16] = 1; masks.append(m)
+    n = len(masks)
+    md = torch.from_numpy(np.stack(masks)).to(DEV)
+    scratch = torch.zeros((n, 5, H * W), dtype=torch.int32, device=DEV)
+    bbox = torch.zeros((n, 4), dtype=torch.int32, device=DEV)
+    L.check(L.lib().pb_ccl_bbox(md.data_ptr(), n, H, W, scratch.data_ptr(), bbox.data_ptr(), L.stream_ptr()))
+    torch.cuda.synchronize()
+    got = bbox.cpu().numpy()
+    for i, mk in enumerate(masks):
+        exp = tuple(OT.heatmap_to_bbox(mk * 255))
+        assert tuple(got[i]) == exp, f"mask {i}: got {tuple(got[i])} expected {exp}"
+
+
+@pytest.mark.parametrize("nc,kpt", [(80, None), (1, (13, 3)), (1, (12, 3)), (1, (13, 2))])
+def test_decode_nms_matches_oracle(nc, kpt):
+    torch.manual_seed(nc + (kpt[0] if kpt else 0))
+    B, shapes = 3, [(48, 80), (24, 40), (12, 20)]
+    nk = kpt[0] * kpt[1] if kpt else 0
+    fC = 64 + nc + nk
+    raws = []
+    for (h, w) in shapes:
+        r = torch.randn(B, fC, h, w)
+        r[:, :64] *= 2.0
+        r[:, 64:64 + nc] = r[:, 64:64 + nc] * 1.5 - (4.0 if nc > 1 else 2.0)
+        raws.append(r)
+    head = OY.PoseHead(nc, kpt, (64, 128, 256)) if kpt else OY.DetectHead(nc, (64, 128, 256))
+    if kpt:
+        y, anc, st = head.decode_boxes(raws)
+        kp = torch.cat([r[:, 64 + nc:].reshape(B, nk, -1) for r in raws], 2)
+        K, D = kpt
+        k = kp.view(B, K, D, -1).clone()
+        k[:, :, 0] = (k[:, :, 0] * 2.0 + (anc[0] - 0.5)) * st
+        k[:, :, 1] = (k[:, :, 1] * 2.0 + (anc[1] - 0.5)) * st
+        if D == 3:
+            k[:, :, 2] = k[:, :, 2].sigmoid()
+        pred = torch.cat([y, k.view(B, nk, -1)], 1)
+    else:
+        pred, _, _ = head.decode_boxes(raws)
+    conf, iou, max_det = 0.5, 0.7, 300
+    classes = [0] if nc > 1 else None
+    exp = OY.non_max_suppression(pred, conf, iou, classes, max_det, nc)
+
+    feats = [r.permute(0, 2, 3, 1).contiguous().to(DEV) for r in raws]
+    lv = (L.YoloLevel * 3)()
+    for l, (f, (h, w), s) in enumerate(zip(feats, shapes, (8, 16, 32))):
+        lv[l].feat, lv[l].h, lv[l].w, lv[l].stride = f.data_ptr(), h, w, s
+    cap, rowlen = 4096, 6 + nk
+    cand = torch.zeros((B, cap, rowlen), device=DEV)
+    anchor = torch.zeros((B, cap), dtype=torch.int32, device=DEV)
+    count = torch.zeros((B,), dtype=torch.int32, device=DEV)
+    L.check(L.lib().pb_yolo_decode(lv, 3, B, fC, nc, nk, kpt[1] if kpt else 0, conf, 0 if nc > 1 else -1,
+                                   cand.data_ptr(), anchor.data_ptr(), count.data_ptr(), cap, L.stream_ptr()))
+    out = torch.zeros((B, max_det, rowlen), device=DEV)
+    ocnt = torch.zeros((B,), dtype=torch.int32, device=DEV)
+    L.check(L.lib().pb_yolo_nms(cand.data_ptr(), anchor.data_ptr(), count.data_ptr(), B, cap, rowlen, iou, max_det,
+                                out.data_ptr(), ocnt.data_ptr(), L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert int(count.max()) <= cap
+    for b in range(B):
+        e = exp[b]
+        n = int(ocnt[b])
+        assert n == e.shape[0], f"image {b}: kept {n} vs oracle {e.shape[0]} (candidates {int(count[b])})"
+        assert n > 3, "test is vacuous"
+        g = out[b, :n].cpu()
+        assert torch.allclose(g, e, rtol=1e-4, atol=2e-3), f"image {b}: max diff {(g-e).abs().max()}"
