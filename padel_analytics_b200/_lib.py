@@ -75,10 +75,7 @@ def lib() -> C.CDLL:
                 "(no CPU fallback exists)")
         l = C.CDLL(str(LIB_PATH))
         for name, (res, args) in SIGNATURES.items():
-            try:
-                fn = getattr(l, name)
-            except AttributeError:  # TEMP during bring-up
-                continue
+            fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
         _lib = l

@@ -76,6 +76,9 @@ class Program:
     def __init__(self):
         self._h = L.lib().pb_program_create()
         self._keep = []  # tensors referenced by raw pointer
+        self.kinds: list[str] = []  # per op: 'conv' | 'pool' | 'up' | 'sppf'
+        self.flops: list[float] = []  # per op: algorithmic FLOPs (2*MACs on the real, unpadded channel counts)
+        self.bytes: list[float] = []  # per op: algorithmic activation bytes (input read once + output written once)
 
     def __del__(self):
         try:
@@ -87,22 +90,37 @@ class Program:
     def keep(self, *tensors):
         self._keep.extend(tensors)
 
-    def conv(self, desc: L.ConvDesc):
+    def conv(self, desc: L.ConvDesc, cin_real: int | None = None, cout_real: int | None = None):
         L.check(L.lib().pb_program_add_conv(self._h, C.byref(desc)))
+        ci = desc.cin if cin_real is None else cin_real
+        co = desc.cout_store if cout_real is None else cout_real
+        ho, wo = desc.H // desc.stride, desc.W // desc.stride
+        self.kinds.append("conv")
+        self.flops.append(2.0 * desc.N * ho * wo * co * ci * desc.ksize * desc.ksize)
+        obytes = 4 if desc.out_mode in (L.OUT_F32_NHWC, L.OUT_F32_NCHW) else 2
+        self.bytes.append(float(desc.N) * (desc.H * desc.W * ci * 2 + ho * wo * co * obytes))
 
     def maxpool2(self, x, c_off, c, out, out_coff):
         N, H, W, Ct = x.shape
         L.check(L.lib().pb_program_add_maxpool2(self._h, x.data_ptr(), N, H, W, Ct, c_off, c, out.data_ptr(),
                                                 out.shape[-1], out_coff))
+        self._note("pool", N * H * W * c * 2 * 1.25)
 
     def upsample2(self, x, c_off, c, out, out_coff):
         N, H, W, Ct = x.shape
         L.check(L.lib().pb_program_add_upsample2(self._h, x.data_ptr(), N, H, W, Ct, c_off, c, out.data_ptr(),
                                                  out.shape[-1], out_coff))
+        self._note("up", N * H * W * c * 2 * 5.0)
 
     def sppf_pool(self, buf, c):
         N, H, W, Ct = buf.shape
         L.check(L.lib().pb_program_add_sppf_pool(self._h, buf.data_ptr(), N, H, W, Ct, c))
+        self._note("sppf", N * H * W * c * 2 * 4.0)
+
+    def _note(self, kind: str, nbytes: float):
+        self.kinds.append(kind)
+        self.flops.append(0.0)
+        self.bytes.append(float(nbytes))
 
     @property
     def num_ops(self) -> int:
@@ -113,3 +131,19 @@ class Program:
             L.check(L.lib().pb_program_run(self._h, L.stream_ptr()))
         else:
             L.check(L.lib().pb_program_run_range(self._h, first, last, L.stream_ptr()))
+
+
+def time_program_ops(prog: Program, repeats: int = 3):
+    """Per-op device time (ms) with CUDA events recorded on the launch stream between consecutive ops."""
+    n = prog.num_ops
+    best = [float("inf")] * n
+    for _ in range(repeats):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        ev[0].record()
+        for i in range(n):
+            prog.run(i, i + 1)
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        for i in range(n):
+            best[i] = min(best[i], ev[i].elapsed_time(ev[i + 1]))
+    return best

@@ -94,7 +94,8 @@ class TrackNetEngine:
 
         def conv(x, coff, cin, name, out, ooff, mode=L.OUT_F16_NHWC, act=R, k=3, store=None):
             w, b = W_[name]
-            P.conv(ops.make_conv_desc(x, coff, cin, w, b, k, 1, act, out, ooff, mode, store))
+            P.conv(ops.make_conv_desc(x, coff, cin, w, b, k, 1, act, out, ooff, mode, store),
+                   cin_real=27 if name == "down_block_1.conv_1" else cin, cout_real=8 if name == "predictor" else None)
 
         conv(self.x, 0, 32, "down_block_1.conv_1", self.t1, 0)
         conv(self.t1, 0, 64, "down_block_1.conv_2", self.cat3, 128)

@@ -133,7 +133,8 @@ class YoloEngine:
         def conv(x, coff, cin, prefix, out, ooff, k, s, res=None, res_off=0):
             cout = self._cout(prefix)
             w, b = self._wb(prefix, cin, ops.pad16(cout))
-            P.conv(ops.make_conv_desc(x, coff, cin, w, b, k, s, SILU, out, ooff, L.OUT_F16_NHWC, None, res, res_off))
+            P.conv(ops.make_conv_desc(x, coff, cin, w, b, k, s, SILU, out, ooff, L.OUT_F16_NHWC, None, res, res_off),
+                   cin_real=self.sd[f"{prefix}.conv.weight"].shape[1], cout_real=cout)
             return ops.pad16(cout)
 
         def c2f(x, coff, cin, i, out, ooff, shortcut):
@@ -208,7 +209,8 @@ class YoloEngine:
                 conv(f, 0, cf, f"{pre}.0", t1, 0, 3, 1)
                 conv(t1, 0, cm, f"{pre}.1", t2, 0, 3, 1)
                 w, b = self._wb(f"{pre}.2", cm, ops.pad16(cout_real), bn=False)
-                P.conv(ops.make_conv_desc(t2, 0, cm, w, b, 1, 1, L.ACT_NONE, feat, off, L.OUT_F32_NHWC, cout_real))
+                P.conv(ops.make_conv_desc(t2, 0, cm, w, b, 1, 1, L.ACT_NONE, feat, off, L.OUT_F32_NHWC, cout_real),
+                       cin_real=self.sd[f"{pre}.2.weight"].shape[1], cout_real=cout_real)
             feats.append(feat)
             levels.append((feat, h, w_, st))
         lv = (L.YoloLevel * 3)()

@@ -148,14 +148,14 @@ class BallTracker(Tracker):
         first = next(stream, None)
         if first is None:
             return {}
-        pipe = self._pipeline(first.shape[:2], median)
+        pipe = self._pipeline(tuple(first.shape[-3:-1]), median)
         pipe.reset(base=first_frame)
         w_scaler, h_scaler = self.video_info.width / self.WIDTH, self.video_info.height / self.HEIGHT  # :379-384
         out: dict[int, tuple[int, int, int]] = {}
         total_windows = total_frames - 7
 
         def push(frames):
-            pipe.push_frames(torch.from_numpy(np.stack(frames)))
+            pipe.push_frames(frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.stack(frames)))
             while True:  # run every window that became computable
                 nb = min(B, pipe.windows_ready(), total_windows - (pipe.base + pipe.n_windows))
                 if nb <= 0:
@@ -167,6 +167,12 @@ class BallTracker(Tracker):
                     if emit_range is None or emit_range[0] <= n < emit_range[1]:
                         out[n] = (xs[i], ys[i], vs[i])
 
+        if isinstance(first, torch.Tensor) and first.dim() == 4:
+            # batched frame source: items are uint8 (n,H,W,3) tensors (pinned host or device), n <= batch_size
+            push(first)
+            for batch in stream:
+                push(batch)
+            return out
         chunk = [first]
         for f in stream:
             if len(chunk) == B:

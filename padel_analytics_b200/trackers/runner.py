@@ -86,7 +86,8 @@ class TrackingRunner:
                 part = (part, hw)
             else:
                 part = list(tracker.predict_and_update(src(lo, hi), total_frames=hi - lo).predictions)
-            torch.cuda.synchronize()
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
             if dist_on:
                 gathered = [None] * world if rank == 0 else None
                 dist.gather_object(part, gathered, dst=0)

@@ -1,0 +1,85 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference code (only possible where /root/reference exists).
+
+    python tests/golden/make_golden.py
+
+ball_ref.npz  — the reference BallTracker.predict_frames TrackNet stage (ball_tracker.py:373-523) on 21 synthetic
+                frames with a seeded TrackNet at a reduced heat-map size (HEIGHT=32, WIDTH=64 are class attributes the
+                reference lets a subclass override): ensemble heat-maps fed to predict_modified and the x/y/visibility
+                it returned, captured by wrapping `predict_modified`.  (predict_frames then dies with KeyError 'Frame',
+                SURVEY App. E q6 — the TrackNet stage has completed by then.)
+tracknet_ref.npz — reference TrackNet forward on one seeded input (models.py:45-74).
+"""
+import sys
+import tempfile
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+from oracle import ref_harness, weights as OW  # noqa: E402
+from padel_analytics_b200 import synth  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def main():
+    ref_harness.import_reference()
+    import trackers.ball_tracker.ball_tracker as rbt
+    from trackers.ball_tracker.models import TrackNet
+
+    torch.manual_seed(0)
+    ck = OW.make_tracknet()
+    with tempfile.TemporaryDirectory() as td:
+        path = Path(td) / "tracknet.pt"
+        torch.save(ck, path)
+
+        class SmallBall(rbt.BallTracker):
+            HEIGHT, WIDTH = 32, 64
+
+        T, B, H, W = 21, 4, 90, 160
+        frames = synth.make_frames(T, H, W, seed=7)
+        med = synth.make_median(H, W, seed=7).numpy()
+        bt = SmallBall(str(path), None, batch_size=B, median=med)
+        bt.video_info_post_init(SimpleNamespace(width=W, height=H, fps=30))
+        cap = {"ens": [], "x": [], "y": [], "vis": []}
+        orig = rbt.predict_modified
+
+        def spy(**kw):
+            out = orig(**kw)
+            cap["ens"].append(kw["y_pred"].clone())
+            cap["x"] += out["x"]
+            cap["y"] += out["y"]
+            cap["vis"] += out["visibility"]
+            return out
+
+        rbt.predict_modified = spy
+        try:
+            bt.predict_frames((f.numpy() for f in frames), total_frames=T)
+        except KeyError as e:  # q6
+            assert str(e) == "'Frame'"
+        finally:
+            rbt.predict_modified = orig
+        ens = torch.cat(cap["ens"])[:, 0].numpy()
+        assert ens.shape[0] == T and len(cap["x"]) == T
+        np.savez_compressed(OUT / "ball_ref.npz", ens=ens.astype(np.float32), x=np.array(cap["x"]),
+                            y=np.array(cap["y"]), vis=np.array(cap["vis"]), T=T, B=B, H=H, W=W, seed=7,
+                            net_h=32, net_w=64)
+        print("ball_ref:", ens.shape, "visible frames", int(np.sum(cap["vis"])), list(zip(cap["x"], cap["y"]))[:8])
+
+    net = TrackNet(27, 8)
+    net.load_state_dict(ck["model"])
+    net.eval()
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand((1, 27, 32, 64), generator=g)
+    with torch.no_grad():
+        y = net(x)
+    np.savez_compressed(OUT / "tracknet_ref.npz", y=y.numpy(), seed=11)
+    print("tracknet_ref:", y.shape, float(y.mean()))
+
+
+if __name__ == "__main__":
+    main()

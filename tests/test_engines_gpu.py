@@ -135,22 +135,30 @@ def test_yolo_heads_and_detections_match_oracle(kind, imgsz, prep):
     for l, r in enumerate(raws):
         got = st["feats"][l][:B].cpu().permute(0, 3, 1, 2)
         err = (got - r).abs()
-        print(kind, "level", l, "raw head max abs err", err.max().item(), "scale", r.abs().mean().item())
-        assert err.max().item() < 0.25
+        rel = err.max().item() / r.abs().max().item()
+        print(kind, "level", l, "raw head max abs err", err.max().item(), "mean", err.mean().item(), "max |ref|",
+              r.abs().max().item(), "rel", rel)
+        assert rel < 0.03  # fp16 activations through ~30 fused conv layers
     # 3) detections
-    tot, hit = 0, 0.0
+    tot, hit, kmax = 0, 0.0, 0.0
     for e, g in zip(exp, res):
         frac, idx = _match(e.boxes.xyxy, g.boxes.xyxy)
         print(kind, "oracle dets", len(e.boxes), "ours", len(g.boxes), "matched(IoU>=.99)", frac)
         tot += len(e.boxes)
         hit += frac * len(e.boxes)
         if e.keypoints is not None and len(e.boxes):
-            d = (e.keypoints.xy - g.keypoints.xy[idx]).norm(dim=-1)
+            d = (e.keypoints.xy - g.keypoints.xy[idx]).norm(dim=-1)  # (N,K) px in the pre-processed image
             ok = (torchvision_iou(e.boxes.xyxy, g.boxes.xyxy[idx]) >= 0.99)
-            if ok.any():
-                print(kind, "keypoint L2 max on matched", d[ok].max().item())
+            # keypoints whose confidence sits on the 0.5 visibility cut may be zeroed on one side only (H4)
+            sure = (e.keypoints.conf - 0.5).abs() > 0.02
+            sel = ok[:, None] & sure
+            if sel.any():
+                scale = max(1920 / imgsz, 1080 / imgsz)  # to original-frame pixels
+                kmax = max(kmax, d[sel].max().item() * scale)
+                print(kind, "keypoint L2 max on matched (frame px)", d[sel].max().item() * scale)
     assert tot > 0, "vacuous: oracle found no detections"
     assert hit / tot >= 0.9
+    assert kmax < 0.5, f"keypoint L2 {kmax} px"
 
 
 def torchvision_iou(a, b):

@@ -1,0 +1,170 @@
+"""CPU: C-ABI surface, host-side tracker logic, sharding maths and the world-size-2 gloo path."""
+import json
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from padel_analytics_b200 import _lib as L
+from padel_analytics_b200.trackers import runner as R
+from padel_analytics_b200.trackers import sv_compat as sv
+from padel_analytics_b200.trackers.ball_tracker import Ball
+from padel_analytics_b200.trackers.keypoints_tracker import Keypoint, Keypoints
+from padel_analytics_b200.trackers.players_keypoints_tracker import PlayerKeypoint, PlayerKeypoints, PlayersKeypoints
+from padel_analytics_b200.trackers.players_tracker import Player, Players
+from padel_analytics_b200.trackers.tracker import Tracker, TrackingResults, sampler
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = (ROOT / "include" / "padel_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    lib = L.lib()  # loads and binds every symbol (AttributeError if one is missing)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.pb_version() >= 100
+    out = subprocess.run(["nm", "-D", str(L.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (pb_[a-z0-9_]+)", out))
+    assert declared <= exported
+
+
+def test_engines_fail_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from padel_analytics_b200.engine.tracknet_engine import TrackNetEngine
+    from padel_analytics_b200.engine.yolo_engine import YoloEngine
+
+    with pytest.raises(L.PbError):
+        TrackNetEngine(None, 1)
+    with pytest.raises(L.PbError):
+        YoloEngine({"model": {}, "nc": 1, "kpt_shape": None}, 1)
+
+
+def test_sampler_and_results():
+    chunks = list(sampler(iter(range(7)), 3))
+    assert chunks == [[0, 1, 2], [3, 4, 5], [6]]  # last partial chunk kept (tracker.py:307-312)
+    r = TrackingResults()
+    r.update([1, 2])
+    r.update([3])
+    assert len(r) == 3 and r.counter == 2 and r.sample_predictions == [3] and list(r) == [1, 2, 3]
+    r.restart()
+    assert len(r) == 0
+
+
+def test_object_json_round_trips():
+    b = Ball(frame=3, xy=(10, 20), visibility=1)
+    rt = Ball.from_json(json.loads(json.dumps(b.serialize())))
+    assert (rt.frame, tuple(rt.xy), rt.visibility, rt.projection) == (3, (10, 20), 1, None)
+    k = Keypoints([Keypoint(id=2, xy=(1.5, 2.5)), Keypoint(id=0, xy=(3.0, 4.0))])
+    assert [x["id"] for x in k.serialize()] == [0, 2]
+    assert tuple(Keypoints.from_json(json.loads(json.dumps(k.serialize())))[2].xy) == (1.5, 2.5)
+    pk = PlayersKeypoints([PlayerKeypoints([PlayerKeypoint(id=i, name=n, xy=(float(i), 1.0))
+                                            for i, n in enumerate(PlayerKeypoints.KEYPOINTS_NAMES)])])
+    rt = PlayersKeypoints.from_json(json.loads(json.dumps(pk.serialize())))
+    assert rt[0]["head"].id == 5 and len(rt[0]) == 13
+    det = sv.Detections(xyxy=np.array([[1., 2., 30., 40.]]), confidence=np.array([0.9]), class_id=np.array([0]),
+                        tracker_id=np.array([7]))
+    p = Players([Player(det)])
+    q = Players.from_json(json.loads(json.dumps(p.serialize())))
+    assert q[0].id == 7 and q[0].feet == (15, 40) and q[0].class_id == 0
+
+
+def test_polygon_zone_and_bytetrack_standins():
+    if sv.HAVE_SUPERVISION:
+        pytest.skip("real supervision installed")
+    zone = sv.PolygonZone(np.array([[10, 10], [100, 10], [100, 100], [10, 100]]), frame_resolution_wh=(200, 200))
+    det = sv.Detections(xyxy=np.array([[20., 20., 40., 60.], [150., 150., 170., 190.]], dtype=np.float32),
+                        confidence=np.array([0.9, 0.8], dtype=np.float32), class_id=np.array([0, 0]))
+    assert zone.trigger(det).tolist() == [True, False]
+    bt = sv.ByteTrack(frame_rate=30)
+    ids = []
+    for t in range(5):
+        d = sv.Detections(xyxy=np.array([[20. + t, 20., 40. + t, 60.], [100., 100. + t, 130., 160. + t]], np.float32),
+                          confidence=np.array([0.9, 0.8], np.float32), class_id=np.array([0, 0]))
+        out = bt.update_with_detections(d)
+        ids.append(sorted(out.tracker_id.tolist()))
+    assert ids[0] == [1, 2] and ids[-1] == [1, 2]
+
+
+def test_shard_maths():
+    for total, world in ((1024, 8), (1000, 3), (10, 4)):
+        spans = [R.shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    assert R.ball_shard_frames(100, 0, 25) == (0, 32)
+    assert R.ball_shard_frames(100, 25, 50) == (18, 57)
+    assert R.ball_shard_frames(100, 75, 100) == (68, 100)
+
+
+class _Echo(Tracker):
+    """Tracker whose 'prediction' for a frame is the frame's first pixel value (stands in for a model on CPU)."""
+    batch_size = 3
+
+    def video_info_post_init(self, vi):
+        return self
+
+    def object(self):
+        return Ball
+
+    def draw_kwargs(self):
+        return {}
+
+    def restart(self):
+        self.results.restart()
+
+    def __str__(self):
+        return "echo"
+
+    def predict_sample(self, sample, **kw):
+        return [int(f[0, 0, 0]) for f in sample]
+
+    def predict_frames(self, gen, **kw):
+        from padel_analytics_b200.trackers.tracker import NoPredictFrames
+
+        raise NoPredictFrames()
+
+
+def _frames(lo, hi):
+    for i in range(lo, hi):
+        yield np.full((2, 2, 3), i, dtype=np.uint8)
+
+
+def test_runner_single_process():
+    t = _Echo()
+    R.TrackingRunner([t]).run(frame_source=_frames, total_frames=10)
+    assert t.results.predictions == list(range(10))
+
+
+def test_runner_world2_gloo(tmp_path):
+    """Two processes over gloo: each handles its contiguous shard, rank 0 assembles frame-ordered results."""
+    script = tmp_path / "w.py"
+    script.write_text(f"""
+import sys, json
+sys.path.insert(0, {str(ROOT)!r}); sys.path.insert(0, {str(ROOT / 'tests')!r})
+import torch.distributed as dist
+from test_host_cpu import _Echo, _frames
+from padel_analytics_b200.trackers import runner as R
+dist.init_process_group('gloo')
+t = _Echo()
+R.TrackingRunner([t]).run(frame_source=_frames, total_frames=11)
+if dist.get_rank() == 0:
+    assert t.results.predictions == list(range(11)), t.results.predictions
+    print('WORLD2_OK')
+else:
+    assert t.results.predictions == []
+dist.destroy_process_group()
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)], capture_output=True,
+                       text=True, env=env, timeout=240)
+    assert "WORLD2_OK" in r.stdout, r.stdout + r.stderr

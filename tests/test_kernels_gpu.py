@@ -74,8 +74,8 @@ def test_tracknet_pack_windows():
     med = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
     x = torch.zeros((B, H, W, 32), dtype=torch.float16, device=DEV)
     first = 7
-    L.check(L.lib().pb_tracknet_pack_windows(torch.from_numpy(frames).to(DEV).data_ptr(), ring, first,
-                                             torch.from_numpy(med).to(DEV).data_ptr(), B, H, W, x.data_ptr(),
+    fd, md = torch.from_numpy(frames).to(DEV), torch.from_numpy(med).to(DEV)
+    L.check(L.lib().pb_tracknet_pack_windows(fd.data_ptr(), ring, first, md.data_ptr(), B, H, W, x.data_ptr(),
                                              L.stream_ptr()))
     torch.cuda.synchronize()
     got = x.cpu().float()
