@@ -216,7 +216,9 @@ def main():
 
     # weights: generated on rank 0, broadcast over NCCL (the only init-time collective)
     if rank == 0:
-        ckpts = {k: OW.make_yolo(k) for k in ("detect", "pose13", "court12")}
+        # sparse heads: a handful of players per frame like a real padel rally (the dense defaults are for parity tests)
+        ckpts = {"detect": OW.make_yolo("detect", cls_mean=-5.0), "pose13": OW.make_yolo("pose13", cls_mean=-5.7),
+                 "court12": OW.make_yolo("court12")}
         ckpts["tracknet"] = OW.make_tracknet()
     else:
         ckpts = None

@@ -37,6 +37,7 @@ extern "C" {
 #define PB_OUT_F16_NHWC_UP2 1 /* same, each pixel replicated 2x2 into a (2Ho, 2Wo) tensor (nearest upsample)  */
 #define PB_OUT_F32_NHWC 2     /* float, channels [out_coff, out_coff+cout_store) of an NHWC float tensor       */
 #define PB_OUT_F32_NCHW 3     /* float, planar (N, cout_store, Ho, Wo)                                         */
+#define PB_OUT_NONE 4         /* nothing stored by the conv itself (only valid with a fused head)              */
 
 const char* pb_last_error(void);
 int pb_version(void);
@@ -63,6 +64,13 @@ typedef struct pb_conv_desc {
   int out_coff;   /* first output channel written                                              */
   int out_mode;   /* PB_OUT_*                                                                  */
   int cout_store; /* channels actually stored (<= cout_pad); f16 modes require a multiple of 8 */
+  /* Optional fused 1x1 head applied to the activated outputs of this conv inside the epilogue (TrackNet predictor,
+   * models.py:55,72-73): head_out[n][j][h][w] = sigmoid(sum_c head_weight[j][c] * y[c] + head_bias[j]), j < head_n <= 8.
+   * Requires cout_pad <= 256 (one N tile).  With out_mode == PB_OUT_NONE the conv's own output is not stored.   */
+  const float* head_weight; /* float [head_n][cout_pad] or NULL */
+  const float* head_bias;   /* float [head_n]                   */
+  int head_n;
+  float* head_out;          /* float (N, head_n, Ho, Wo)        */
 } pb_conv_desc;
 
 /* One-shot launches (plan + run). The *_reference variant is a plain CUDA-core kernel used by tests to

@@ -87,7 +87,7 @@ def make_tracknet(seed: int = SEEDS["tracknet"], frac_above: float = 1e-2) -> di
     return {"param_dict": {"seq_len": 8, "bg_mode": "concat"}, "model": net.state_dict()}
 
 
-def make_yolo(kind: str, scale: str = "n", seed: int | None = None) -> dict:
+def make_yolo(kind: str, scale: str = "n", seed: int | None = None, cls_mean: float | None = None) -> dict:
     """kind: 'detect' (nc=80), 'pose13' (nc=1, 13x3 kpts), 'court12' (nc=1, 12x3 kpts).  Last layers are
     standardised on a calibration image so that O(1%) of the anchors exceed the trackers' confidence thresholds
      with varied box sizes; for 'detect' class 0 (person) dominates the other 79."""
@@ -98,7 +98,10 @@ def make_yolo(kind: str, scale: str = "n", seed: int | None = None) -> dict:
     head = net.model[22]
     with torch.no_grad():
         feats = net.features(_calib_yolo_input())
-    cls_mean = {"detect": -2.8, "pose13": -4.2, "court12": -3.4}[kind]
+    # default: dense detections (parity tests want many candidates); bench.py passes a lower cls_mean so that a
+    # frame yields a realistic handful of players
+    if cls_mean is None:
+        cls_mean = {"detect": -2.8, "pose13": -4.2, "court12": -3.4}[kind]
     for l in range(3):
         with torch.no_grad():
             hb = head.cv2[l][1](head.cv2[l][0](feats[l]))

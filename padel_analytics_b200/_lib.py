@@ -25,6 +25,7 @@ class ConvDesc(C.Structure):
         ("res", C.c_void_p), ("res_C", C.c_int), ("res_coff", C.c_int),
         ("out", C.c_void_p), ("out_C", C.c_int), ("out_coff", C.c_int), ("out_mode", C.c_int),
         ("cout_store", C.c_int),
+        ("head_weight", C.c_void_p), ("head_bias", C.c_void_p), ("head_n", C.c_int), ("head_out", C.c_void_p),
     ]
 
 
@@ -33,7 +34,7 @@ class YoloLevel(C.Structure):
 
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_SIGMOID = 0, 1, 2, 3
-OUT_F16_NHWC, OUT_F16_NHWC_UP2, OUT_F32_NHWC, OUT_F32_NCHW = 0, 1, 2, 3
+OUT_F16_NHWC, OUT_F16_NHWC_UP2, OUT_F32_NHWC, OUT_F32_NCHW, OUT_NONE = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); must list every symbol of include/padel_b200.h (tests check this)
 _i, _p, _f = C.c_int, C.c_void_p, C.c_float

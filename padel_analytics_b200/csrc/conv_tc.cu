@@ -25,8 +25,8 @@ namespace pb {
 struct ConvSmemTail {
   uint64_t full[kConvMaxStages];
   uint64_t empty[kConvMaxStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[kConvMaxAcc];
+  uint64_t tmem_empty[kConvMaxAcc];
   uint32_t tmem_base;
 };
 
@@ -59,7 +59,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&tail->full[i], 1);
       mbar_init(&tail->empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kp.acc_stages; ++i) {
       mbar_init(&tail->tmem_full[i], 1);
       mbar_init(&tail->tmem_empty[i], 4);  // one arrive per epilogue warp
     }
@@ -121,7 +121,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
         mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kp.acc_cols);
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&tail->full[stage], phase);
           tc_fence_after();
@@ -142,7 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         umma_commit(&tail->tmem_full[acc]);  // accumulator ready for the epilogue
-        if (++acc == 2) {
+        if (++acc == kp.acc_stages) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -175,7 +175,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
       mbar_wait(&tail->tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kp.acc_cols);
+      float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // fused 1x1 head partial sums
       for (int c = 0; c < kp.BN; c += 16) {
         uint32_t r[16];
         tmem_ld16(t_addr + (uint32_t)c, r);
@@ -203,6 +204,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const float2 f = __half22float2(h2[j]);
                 v[8 * g + 2 * j] += f.x;
                 v[8 * g + 2 * j + 1] += f.y;
+              }
+            }
+          }
+          if (kp.head_n > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j < kp.head_n) {
+                const float4* w4 = reinterpret_cast<const float4*>(kp.head_w + (size_t)j * kp.BN + c);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 w = __ldg(w4 + q);
+                  hacc[j] = fmaf(w.x, v[4 * q], fmaf(w.y, v[4 * q + 1], fmaf(w.z, v[4 * q + 2], fmaf(w.w, v[4 * q + 3], hacc[j]))));
+                }
               }
             }
           }
@@ -234,7 +248,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (ch0 + j < kp.cout_store) op[j] = v[j];
-          } else {  // PB_OUT_F32_NCHW
+          } else if (kp.out_mode == PB_OUT_F32_NCHW) {
             float* ob = reinterpret_cast<float*>(kp.out);
             const size_t plane = (size_t)kp.Ho * kp.Wo;
             const size_t base = (size_t)n * kp.cout_store * plane + (size_t)oh * kp.Wo + ow;
@@ -247,7 +261,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
-      if (++acc == 2) {
+      if (kp.head_n > 0 && valid) {
+        const size_t plane = (size_t)kp.Ho * kp.Wo;
+        float* ho = kp.head_out + (size_t)n * kp.head_n * plane + (size_t)oh * kp.Wo + ow;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < kp.head_n) ho[(size_t)j * plane] = __fdividef(1.f, 1.f + __expf(-(hacc[j] + __ldg(kp.head_b + j))));
+      }
+      if (++acc == kp.acc_stages) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -298,10 +319,18 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   PB_CHECK(d->C % 8 == 0 && d->c_in_off >= 0 && d->c_in_off + d->cin <= d->C, "conv: bad input channel slice");
   PB_CHECK(d->c_in_off % 8 == 0, "conv: c_in_off must be a multiple of 8");
   PB_CHECK((reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0 &&
-               (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+               (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0 &&
+               (d->out_mode == PB_OUT_NONE || (reinterpret_cast<uintptr_t>(d->out) & 15) == 0),
            "conv: pointers must be 16-byte aligned");
   PB_CHECK(d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0), "conv: stride 2 needs even H and W");
   PB_CHECK(d->cout_store > 0 && d->cout_store <= d->cout_pad, "conv: bad cout_store");
+  PB_CHECK(d->out_mode >= PB_OUT_F16_NHWC && d->out_mode <= PB_OUT_NONE, "conv: bad out_mode");
+  PB_CHECK(d->out_mode != PB_OUT_NONE || d->head_n > 0, "conv: PB_OUT_NONE needs a fused head");
+  if (d->head_n > 0) {
+    PB_CHECK(d->head_n <= 8 && d->head_weight && d->head_bias && d->head_out, "conv: bad fused head");
+    PB_CHECK(d->cout_pad <= 256 && d->cout_store == d->cout_pad, "conv: fused head needs a single full N tile");
+    PB_CHECK((reinterpret_cast<uintptr_t>(d->head_weight) & 15) == 0, "conv: head_weight must be 16-byte aligned");
+  }
   const bool f16out = d->out_mode == PB_OUT_F16_NHWC || d->out_mode == PB_OUT_F16_NHWC_UP2;
   if (f16out) {
     PB_CHECK(d->cout_store % 8 == 0 && d->out_coff % 8 == 0 && d->out_C % 8 == 0,
@@ -384,6 +413,15 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   kp.out_coff = d->out_coff;
   kp.out_mode = d->out_mode;
   kp.cout_store = d->cout_store;
+  kp.head_w = d->head_weight;
+  kp.head_b = d->head_bias;
+  kp.head_n = d->head_n;
+  kp.head_out = d->head_out;
+  // TMEM accumulator ring: as many buffers as fit (<= 8) so short-K tiles are not bound by the
+  // MMA -> epilogue -> MMA hand-shake latency
+  kp.acc_cols = (kp.BN + 31) / 32 * 32;
+  kp.acc_stages = 512 / kp.acc_cols;
+  if (kp.acc_stages > kConvMaxAcc) kp.acc_stages = kConvMaxAcc;
   kp.idesc = umma_idesc_f16(kp.BN, 0);
   kp.a_bytes = 128u * kp.KB * 2u;
   kp.b_tx_bytes = (uint32_t)kp.BN * kp.KB * 2u;
@@ -487,9 +525,12 @@ __global__ void conv_reference_kernel(pb_conv_desc d, int Ho, int Wo) {
         }
     } else if (d.out_mode == PB_OUT_F32_NHWC) {
       reinterpret_cast<float*>(d.out)[pix * d.out_C + d.out_coff + co] = v;
-    } else {
+    } else if (d.out_mode == PB_OUT_F32_NCHW) {
       reinterpret_cast<float*>(d.out)[(((size_t)n * d.cout_store + co) * Ho + oh) * Wo + ow] = v;
     }
+    if (d.head_n > 0)  // tests only: head_out pre-zeroed by the caller, receives the pre-sigmoid sums (no bias)
+      for (int j = 0; j < d.head_n; ++j)
+        atomicAdd(d.head_out + (((size_t)n * d.head_n + j) * Ho + oh) * Wo + ow, d.head_weight[j * d.cout_pad + co] * v);
   }
 }
 

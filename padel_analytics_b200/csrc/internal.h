@@ -37,6 +37,7 @@ int num_sms();
 
 // ---- conv plan (built once per layer; holds TMA descriptors + launch geometry) -------------------------------
 constexpr int kConvMaxStages = 12;
+constexpr int kConvMaxAcc = 8;
 constexpr int kConvThreads = 192;  // warp0: TMA producer, warp1: UMMA issuer, warps 2-5: epilogue
 
 struct ConvKParams {
@@ -54,6 +55,11 @@ struct ConvKParams {
   int out_C, out_coff, out_mode, cout_store;
   uint32_t idesc;
   uint32_t a_bytes, b_bytes, b_tx_bytes;
+  int acc_stages, acc_cols;  // TMEM accumulator ring: acc_stages buffers, acc_cols columns apart
+  const float* head_w;
+  const float* head_b;
+  int head_n;
+  float* head_out;
 };
 
 struct ConvPlan {

@@ -42,7 +42,8 @@ def pack_conv_weight(w: torch.Tensor, b: torch.Tensor | None, cin_pad: int, cout
 
 def make_conv_desc(x: torch.Tensor, c_in_off: int, cin: int, w: torch.Tensor, b: torch.Tensor, ksize: int,
                    stride: int, act: int, out: torch.Tensor, out_coff: int, out_mode: int = L.OUT_F16_NHWC,
-                   cout_store: int | None = None, res: torch.Tensor | None = None, res_coff: int = 0) -> L.ConvDesc:
+                   cout_store: int | None = None, res: torch.Tensor | None = None, res_coff: int = 0,
+                   head: tuple | None = None) -> L.ConvDesc:
     """x: NHWC half tensor (N,H,W,C). w: packed half [taps][cout_pad][cin]. out: NHWC tensor (half or float), or
     (N,C,H,W) float for OUT_F32_NCHW."""
     N, H, W, Ct = x.shape
@@ -58,6 +59,15 @@ def make_conv_desc(x: torch.Tensor, c_in_off: int, cin: int, w: torch.Tensor, b:
         d.res, d.res_C, d.res_coff = res.data_ptr(), res.shape[-1], res_coff
     else:
         d.res, d.res_C, d.res_coff = None, 0, 0
+    if head is not None:  # (weight float [n][cout_pad], bias float [n], out float (N,n,Ho,Wo))
+        hw_, hb_, ho_ = head
+        assert hw_.dtype == torch.float32 and hw_.shape[1] == cout_pad and hw_.is_contiguous()
+        d.head_weight, d.head_bias, d.head_n, d.head_out = hw_.data_ptr(), hb_.data_ptr(), hw_.shape[0], ho_.data_ptr()
+    if out_mode == L.OUT_NONE:
+        d.out, d.out_C = None, 0
+        d.out_coff, d.out_mode = 0, out_mode
+        d.cout_store = cout_pad
+        return d
     d.out = out.data_ptr()
     d.out_C = out.shape[-1] if out_mode != L.OUT_F32_NCHW else out.shape[1]
     d.out_coff, d.out_mode = out_coff, out_mode
@@ -76,6 +86,7 @@ class Program:
     def __init__(self):
         self._h = L.lib().pb_program_create()
         self._keep = []  # tensors referenced by raw pointer
+        self.descs: list = []  # per op: ConvDesc copy (convs) or None
         self.kinds: list[str] = []  # per op: 'conv' | 'pool' | 'up' | 'sppf'
         self.flops: list[float] = []  # per op: algorithmic FLOPs (2*MACs on the real, unpadded channel counts)
         self.bytes: list[float] = []  # per op: algorithmic activation bytes (input read once + output written once)
@@ -96,6 +107,7 @@ class Program:
         co = desc.cout_store if cout_real is None else cout_real
         ho, wo = desc.H // desc.stride, desc.W // desc.stride
         self.kinds.append("conv")
+        self.descs.append(desc)
         self.flops.append(2.0 * desc.N * ho * wo * co * ci * desc.ksize * desc.ksize)
         obytes = 4 if desc.out_mode in (L.OUT_F32_NHWC, L.OUT_F32_NCHW) else 2
         self.bytes.append(float(desc.N) * (desc.H * desc.W * ci * 2 + ho * wo * co * obytes))
@@ -119,6 +131,7 @@ class Program:
 
     def _note(self, kind: str, nbytes: float):
         self.kinds.append(kind)
+        self.descs.append(None)
         self.flops.append(0.0)
         self.bytes.append(float(nbytes))
 

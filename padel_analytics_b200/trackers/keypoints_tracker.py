@@ -118,8 +118,9 @@ class KeypointsTracker(Tracker):
         for result in results:
             kps = []
             if len(result.keypoints.xy):
-                for i, kp in enumerate(result.keypoints.xy[0]):
-                    kps.append(Keypoint(id=self.POINTS_MAPPER[i], xy=(kp[0].item() * ratio_x, kp[1].item() * ratio_y)))
+                xy = result.keypoints.xy[0].numpy().astype(np.float64) * np.array([ratio_x, ratio_y])
+                for i, (x, y) in enumerate(xy.tolist()):
+                    kps.append(Keypoint(id=self.POINTS_MAPPER[i], xy=(x, y)))
             out.append(Keypoints(kps))
         return out
 

@@ -143,13 +143,12 @@ class PlayerKeypointsTracker(Tracker):
         ratio_x = frame_hw[1] / self.train_image_size
         ratio_y = frame_hw[0] / self.train_image_size
         out = []
+        names = PlayerKeypoints.KEYPOINTS_NAMES
         for result in results:
-            players = []
-            for det in result.keypoints.xy:  # (K,2) per player
-                players.append(PlayerKeypoints([
-                    PlayerKeypoint(id=i, name=PlayerKeypoints.KEYPOINTS_NAMES[i],
-                                   xy=(kp[0].item() * ratio_x, kp[1].item() * ratio_y))
-                    for i, kp in enumerate(det)]))
+            # float32 -> Python float (exact) * Python float ratio, as `keypoint[0].item() * ratio_x` does (:306-309)
+            xy = result.keypoints.xy.numpy().astype(np.float64) * np.array([ratio_x, ratio_y])
+            players = [PlayerKeypoints([PlayerKeypoint(id=i, name=names[i], xy=(x, y)) for i, (x, y) in enumerate(det)])
+                       for det in xy.tolist()]
             out.append(PlayersKeypoints(players))
         return out
 

@@ -105,3 +105,23 @@ def test_reference_kernel_matches_torch(case):
 def test_tcgen05_conv_matches_torch(case):
     bad, mx = run_case(**case)
     assert bad == 0.0, f"tcgen05 kernel: {bad*100:.3f}% elements out of tolerance (max err {mx})"
+
+
+def test_fused_1x1_head_matches_torch():
+    """conv3x3+ReLU with the TrackNet predictor (1x1, 8 outputs, sigmoid) fused into the epilogue."""
+    g = torch.Generator().manual_seed(5)
+    N, H, W, cin, cout = 2, 16, 128, 64, 64
+    x = torch.randn(N, H, W, cin, generator=g).half()
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    hw = torch.randn(8, cout, generator=g) * 0.3
+    hb = torch.randn(8, generator=g) * 0.1
+    wp, bp = ops.pack_conv_weight(w, b, cin, cout, "cuda")
+    out = torch.zeros((N, 8, H, W), device="cuda")
+    d = ops.make_conv_desc(x.cuda(), 0, cin, wp, bp, 3, 1, L.ACT_RELU, None, 0, L.OUT_NONE,
+                           head=(hw.cuda().contiguous(), hb.cuda(), out))
+    ops.conv2d(d)
+    torch.cuda.synchronize()
+    y = torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), b, padding=1))
+    exp = torch.sigmoid(F.conv2d(y, hw.view(8, cout, 1, 1), hb))
+    assert (out.cpu() - exp).abs().max().item() < 2e-3
