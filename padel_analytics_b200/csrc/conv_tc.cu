@@ -28,13 +28,124 @@ struct ConvSmemTail {
   uint64_t tmem_full[kConvMaxAcc];
   uint64_t tmem_empty[kConvMaxAcc];
   uint32_t tmem_base;
+  uint32_t pad_[3];
+  float bias[kConvMaxCout];  // staged once per CTA
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == PB_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == PB_ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
-  if (act == PB_ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-v));
-  return v;
+struct TileCoord {
+  int nt, tw, th, tn;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& kp, int tile) {
+  TileCoord c;
+  int t = tile;
+  c.nt = t % kp.n_ntiles;
+  t /= kp.n_ntiles;
+  c.tw = t % kp.tiles_w;
+  t /= kp.tiles_w;
+  c.th = t % kp.tiles_h;
+  c.tn = t / kp.tiles_h;
+  return c;
+}
+
+// bias + activation on 16 accumulator columns; `act` is CTA-uniform and each case is a straight unrolled loop so
+// the 16 independent MUFU chains interleave
+__device__ __forceinline__ void bias_act16(const uint32_t (&r)[16], const float* __restrict__ sbias, int act,
+                                           float (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * q);
+    v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b.x;
+    v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b.y;
+    v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
+    v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
+  }
+  if (act == PB_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
+  } else if (act == PB_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == PB_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+  }
+}
+
+struct EpiPix {
+  bool valid;
+  int n, oh, ow;
+  size_t pix;
+};
+
+// residual / fused head / store of 16 activated channels starting at output channel ch0 (c = column in the N tile)
+__device__ __forceinline__ void epilogue_store16(const ConvKParams& kp, const EpiPix& px, int ch0, int c,
+                                                 float (&v)[16], float (&hacc)[8]) {
+  if (kp.res != nullptr) {
+    const uint4* rp = reinterpret_cast<const uint4*>(kp.res + px.pix * kp.res_C + kp.res_coff + ch0);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const uint4 rv = __ldg(rp + g);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        v[8 * g + 2 * j] += f.x;
+        v[8 * g + 2 * j + 1] += f.y;
+      }
+    }
+  }
+  if (kp.head_n > 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < kp.head_n) {
+        const float4* w4 = reinterpret_cast<const float4*>(kp.head_w + (size_t)j * kp.BN + c);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; q += 2) {
+          const float4 wa = __ldg(w4 + q), wb = __ldg(w4 + q + 1);
+          s0 = fmaf(wa.x, v[4 * q], fmaf(wa.y, v[4 * q + 1], fmaf(wa.z, v[4 * q + 2], fmaf(wa.w, v[4 * q + 3], s0))));
+          s1 = fmaf(wb.x, v[4 * q + 4], fmaf(wb.y, v[4 * q + 5], fmaf(wb.z, v[4 * q + 6], fmaf(wb.w, v[4 * q + 7], s1))));
+        }
+        hacc[j] += s0 + s1;
+      }
+    }
+  }
+  if (kp.out_mode == PB_OUT_F16_NHWC || kp.out_mode == PB_OUT_F16_NHWC_UP2) {
+    uint4 pk[2];
+    __half2* h2 = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h2[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    __half* ob = reinterpret_cast<__half*>(kp.out);
+    const bool two = (kp.cout_store - ch0 >= 16);  // cout_store is a multiple of 8
+    if (kp.out_mode == PB_OUT_F16_NHWC) {
+      uint4* op = reinterpret_cast<uint4*>(ob + px.pix * kp.out_C + kp.out_coff + ch0);
+      op[0] = pk[0];
+      if (two) op[1] = pk[1];
+    } else {
+      const int Wo2 = kp.Wo * 2;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t pix2 = ((size_t)px.n * (kp.Ho * 2) + (px.oh * 2 + dy)) * Wo2 + (px.ow * 2 + dx);
+          uint4* op = reinterpret_cast<uint4*>(ob + pix2 * kp.out_C + kp.out_coff + ch0);
+          op[0] = pk[0];
+          if (two) op[1] = pk[1];
+        }
+    }
+  } else if (kp.out_mode == PB_OUT_F32_NHWC) {
+    float* op = reinterpret_cast<float*>(kp.out) + px.pix * kp.out_C + kp.out_coff + ch0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (ch0 + j < kp.cout_store) op[j] = v[j];
+  } else if (kp.out_mode == PB_OUT_F32_NCHW) {
+    float* ob = reinterpret_cast<float*>(kp.out);
+    const size_t plane = (size_t)kp.Ho * kp.Wo;
+    const size_t base = (size_t)px.n * kp.cout_store * plane + (size_t)px.oh * kp.Wo + px.ow;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (ch0 + j < kp.cout_store) ob[base + (size_t)(ch0 + j) * plane] = v[j];
+  }
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -50,13 +161,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int k_iters = kp.taps * kp.kblocks;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_w);
-  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_a);
+  if (warp == 6 && lane == 0) tma_prefetch_desc(&tmap_w);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kp.stages; ++i) {
-      mbar_init(&tail->full[i], 1);
+      mbar_init(&tail->full[i], 2);  // A producer + B producer (each arrives with its expected bytes)
       mbar_init(&tail->empty[i], 1);
     }
     for (int i = 0; i < kp.acc_stages; ++i) {
@@ -69,37 +178,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tmem_alloc(&tail->tmem_base, 512);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < kp.cout_pad; i += blockDim.x) tail->bias[i] = kp.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
   if (warp == 0) {
-    // ============================== TMA producer ==============================
+    // ============================== TMA producer: activations ==============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const int TW = 1 << kp.tw_log2, TH = 1 << kp.th_log2;
       const int TN = 128 >> (kp.tw_log2 + kp.th_log2);
       for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int nt = t % kp.n_ntiles;
-        t /= kp.n_ntiles;
-        const int tw = t % kp.tiles_w;
-        t /= kp.tiles_w;
-        const int th = t % kp.tiles_h;
-        const int tn = t / kp.tiles_h;
+        const TileCoord tc = decode_tile(kp, tile);
+        const int seq = (tile - blockIdx.x) / gridDim.x;
+        const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
+        if (dbg) kp.dbg[(0 * 64 + seq) * 4 + 0] = clock64();
         for (int tap = 0; tap < kp.taps; ++tap) {
-          const int cw = tw * TW + kp.tap_dw[tap];
-          const int ch = th * TH + kp.tap_dh[tap];
+          const int cw = tc.tw * TW + kp.tap_dw[tap];
+          const int ch = tc.th * TH + kp.tap_dh[tap];
           const int cc = kp.c_in_off + kp.tap_dc[tap];
           for (int kb = 0; kb < kp.kblocks; ++kb) {
             mbar_wait(&tail->empty[stage], phase ^ 1);
-            uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
-            uint8_t* b_dst = a_dst + kp.a_bytes;
-            mbar_arrive_expect_tx(&tail->full[stage], kp.a_bytes + kp.b_tx_bytes);
-            tma_load_5d(a_dst, &tmap_a, &tail->full[stage], cc + kb * kp.KB, cw, kp.tap_d2[tap], ch, tn * TN);
-            tma_load_3d(b_dst, &tmap_w, &tail->full[stage], kb * kp.KB, nt * kp.BN, tap);
+            mbar_arrive_expect_tx(&tail->full[stage], kp.a_bytes);
+            tma_load_5d(smem + (size_t)stage * stage_bytes, &tmap_a, &tail->full[stage], cc + kb * kp.KB, cw,
+                        kp.tap_d2[tap], ch, tc.tn * TN);
+            if (++stage == kp.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        if (dbg) kp.dbg[(0 * 64 + seq) * 4 + 1] = clock64();
+      }
+    }
+    __syncwarp();
+  } else if (warp == 6) {
+    // ============================== TMA producer: weights (issued in parallel with warp 0) =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+        const int nt = tile % kp.n_ntiles;
+        for (int tap = 0; tap < kp.taps; ++tap) {
+          for (int kb = 0; kb < kp.kblocks; ++kb) {
+            mbar_wait(&tail->empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&tail->full[stage], kp.b_tx_bytes);
+            tma_load_3d(smem + (size_t)stage * stage_bytes + kp.a_bytes, &tmap_w, &tail->full[stage], kb * kp.KB,
+                        nt * kp.BN, tap);
             if (++stage == kp.stages) {
               stage = 0;
               phase ^= 1;
@@ -119,12 +247,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t swz = (uint32_t)kp.KB * 2u;
       const int ksteps = kp.KB / 16;
       for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+        const int seq = (tile - blockIdx.x) / gridDim.x;
+        const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
+        if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 0] = clock64();
         mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kp.acc_cols);
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&tail->full[stage], phase);
           tc_fence_after();
+          if (dbg && it == 0) kp.dbg[(1 * 64 + seq) * 4 + 2] = clock64();
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t b_addr = a_addr + kp.a_bytes;
           const uint64_t adesc = umma_desc_kmajor(a_addr, swz);
@@ -142,6 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         umma_commit(&tail->tmem_full[acc]);  // accumulator ready for the epilogue
+        if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 3] = clock64();
         if (++acc == kp.acc_stages) {
           acc = 0;
           acc_phase ^= 1;
@@ -150,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ============================== epilogue (4 warps, one TMEM lane quarter each) ==============================
+    // ============================== epilogue (warps 2-5, one TMEM lane quarter each) ==========================
     const int quarter = warp & 3;
     const int p = quarter * 32 + lane;  // row of the M=128 tile handled by this thread
     const int TWm = (1 << kp.tw_log2) - 1, THm = (1 << kp.th_log2) - 1;
@@ -160,110 +294,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
-      int t = tile;
-      const int nt = t % kp.n_ntiles;
-      t /= kp.n_ntiles;
-      const int tw = t % kp.tiles_w;
-      t /= kp.tiles_w;
-      const int th = t % kp.tiles_h;
-      const int tn = t / kp.tiles_h;
-      const int ow = (tw << kp.tw_log2) + tw_i;
-      const int oh = (th << kp.th_log2) + th_i;
-      const int n = tn * (128 >> (kp.tw_log2 + kp.th_log2)) + tn_i;
-      const bool valid = (ow < kp.Wo) && (oh < kp.Ho) && (n < kp.N);
-      const size_t pix = ((size_t)n * kp.Ho + oh) * kp.Wo + ow;
-
+      const TileCoord tc = decode_tile(kp, tile);
+      EpiPix px;
+      px.ow = (tc.tw << kp.tw_log2) + tw_i;
+      px.oh = (tc.th << kp.th_log2) + th_i;
+      px.n = tc.tn * (128 >> (kp.tw_log2 + kp.th_log2)) + tn_i;
+      px.valid = (px.ow < kp.Wo) && (px.oh < kp.Ho) && (px.n < kp.N);
+      px.pix = ((size_t)px.n * kp.Ho + px.oh) * kp.Wo + px.ow;
+      const int seq = (tile - blockIdx.x) / gridDim.x;
+      const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64 && threadIdx.x == 64;
+      if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 0] = clock64();
       mbar_wait(&tail->tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 1] = clock64();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kp.acc_cols);
       float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // fused 1x1 head partial sums
-      for (int c = 0; c < kp.BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_addr + (uint32_t)c, r);
+      const float* sb = tail->bias + tc.nt * kp.BN;
+      for (int c = 0; c < kp.BN; c += 32) {
+        // two 16-column TMEM loads in flight, one wait
+        uint32_t r0[16], r1[16];
+        const bool second = (c + 16 < kp.BN);
+        tmem_ld16(t_addr + (uint32_t)c, r0);
+        if (second) tmem_ld16(t_addr + (uint32_t)(c + 16), r1);
         tmem_ld_wait();
-        const int ch0 = nt * kp.BN + c;  // first output channel of this chunk
-        if (valid && ch0 < kp.cout_store) {
+        const int ch0 = tc.nt * kp.BN + c;
+        if (px.valid && ch0 < kp.cout_store) {
           float v[16];
-          const float4* b4 = reinterpret_cast<const float4*>(kp.bias + ch0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b = __ldg(b4 + q);
-            v[4 * q + 0] = apply_act(__uint_as_float(r[4 * q + 0]) + b.x, kp.act);
-            v[4 * q + 1] = apply_act(__uint_as_float(r[4 * q + 1]) + b.y, kp.act);
-            v[4 * q + 2] = apply_act(__uint_as_float(r[4 * q + 2]) + b.z, kp.act);
-            v[4 * q + 3] = apply_act(__uint_as_float(r[4 * q + 3]) + b.w, kp.act);
-          }
-          if (kp.res != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(kp.res + pix * kp.res_C + kp.res_coff + ch0);
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const uint4 rv = __ldg(rp + g);
-              const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h2[j]);
-                v[8 * g + 2 * j] += f.x;
-                v[8 * g + 2 * j + 1] += f.y;
-              }
-            }
-          }
-          if (kp.head_n > 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (j < kp.head_n) {
-                const float4* w4 = reinterpret_cast<const float4*>(kp.head_w + (size_t)j * kp.BN + c);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 w = __ldg(w4 + q);
-                  hacc[j] = fmaf(w.x, v[4 * q], fmaf(w.y, v[4 * q + 1], fmaf(w.z, v[4 * q + 2], fmaf(w.w, v[4 * q + 3], hacc[j]))));
-                }
-              }
-            }
-          }
-          if (kp.out_mode == PB_OUT_F16_NHWC || kp.out_mode == PB_OUT_F16_NHWC_UP2) {
-            uint4 pk[2];
-            __half2* h2 = reinterpret_cast<__half2*>(pk);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) h2[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            __half* ob = reinterpret_cast<__half*>(kp.out);
-            const int ngrp = (kp.cout_store - ch0 >= 16) ? 2 : 1;  // cout_store is a multiple of 8
-            if (kp.out_mode == PB_OUT_F16_NHWC) {
-              uint4* op = reinterpret_cast<uint4*>(ob + pix * kp.out_C + kp.out_coff + ch0);
-              op[0] = pk[0];
-              if (ngrp == 2) op[1] = pk[1];
-            } else {
-              const int Wo2 = kp.Wo * 2;
-#pragma unroll
-              for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                  const size_t pix2 = ((size_t)n * (kp.Ho * 2) + (oh * 2 + dy)) * Wo2 + (ow * 2 + dx);
-                  uint4* op = reinterpret_cast<uint4*>(ob + pix2 * kp.out_C + kp.out_coff + ch0);
-                  op[0] = pk[0];
-                  if (ngrp == 2) op[1] = pk[1];
-                }
-            }
-          } else if (kp.out_mode == PB_OUT_F32_NHWC) {
-            float* op = reinterpret_cast<float*>(kp.out) + pix * kp.out_C + kp.out_coff + ch0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (ch0 + j < kp.cout_store) op[j] = v[j];
-          } else if (kp.out_mode == PB_OUT_F32_NCHW) {
-            float* ob = reinterpret_cast<float*>(kp.out);
-            const size_t plane = (size_t)kp.Ho * kp.Wo;
-            const size_t base = (size_t)n * kp.cout_store * plane + (size_t)oh * kp.Wo + ow;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (ch0 + j < kp.cout_store) ob[base + (size_t)(ch0 + j) * plane] = v[j];
-          }
+          bias_act16(r0, sb + c, kp.act, v);
+          epilogue_store16(kp, px, ch0, c, v, hacc);
+        }
+        if (second && px.valid && ch0 + 16 < kp.cout_store) {
+          float v[16];
+          bias_act16(r1, sb + c + 16, kp.act, v);
+          epilogue_store16(kp, px, ch0 + 16, c + 16, v, hacc);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
-      if (kp.head_n > 0 && valid) {
+      if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 2] = clock64();
+      if (kp.head_n > 0 && px.valid) {
         const size_t plane = (size_t)kp.Ho * kp.Wo;
-        float* ho = kp.head_out + (size_t)n * kp.head_n * plane + (size_t)oh * kp.Wo + ow;
+        float* ho = kp.head_out + (size_t)px.n * kp.head_n * plane + (size_t)px.oh * kp.Wo + px.ow;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (j < kp.head_n) ho[(size_t)j * plane] = __fdividef(1.f, 1.f + __expf(-(hacc[j] + __ldg(kp.head_b + j))));
@@ -309,12 +381,16 @@ static int ilog2(int v) {
   return l;
 }
 
+static long long* g_conv_dbg = nullptr;  // set through pb_debug_conv_timeline (bring-up only)
+extern "C" void pb_debug_conv_timeline(long long* buf) { g_conv_dbg = buf; }
+
 int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   PB_CHECK(d && plan, "conv: null argument");
   PB_CHECK(d->ksize == 1 || d->ksize == 3, "conv: ksize %d unsupported", d->ksize);
   PB_CHECK(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
   PB_CHECK(!(d->stride == 2 && d->ksize == 1), "conv: 1x1 stride-2 unsupported");
   PB_CHECK(d->cin > 0 && d->cin % 16 == 0, "conv: cin %d must be a positive multiple of 16", d->cin);
+  PB_CHECK(d->cout_pad <= kConvMaxCout, "conv: cout_pad %d > %d", d->cout_pad, kConvMaxCout);
   PB_CHECK(d->cout_pad > 0 && d->cout_pad % 16 == 0, "conv: cout_pad %d must be a multiple of 16", d->cout_pad);
   PB_CHECK(d->C % 8 == 0 && d->c_in_off >= 0 && d->c_in_off + d->cin <= d->C, "conv: bad input channel slice");
   PB_CHECK(d->c_in_off % 8 == 0, "conv: c_in_off must be a multiple of 8");
@@ -348,6 +424,7 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   plan->desc = *d;
   ConvKParams& kp = plan->kp;
   memset(&kp, 0, sizeof(kp));
+  kp.cout_pad = d->cout_pad;
   const int s = d->stride;
   kp.N = d->N;
   kp.Ho = d->H / s;
@@ -417,6 +494,7 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   kp.head_b = d->head_bias;
   kp.head_n = d->head_n;
   kp.head_out = d->head_out;
+  kp.dbg = g_conv_dbg;
   // TMEM accumulator ring: as many buffers as fit (<= 8) so short-K tiles are not bound by the
   // MMA -> epilogue -> MMA hand-shake latency
   kp.acc_cols = (kp.BN + 31) / 32 * 32;

@@ -38,13 +38,14 @@ int num_sms();
 // ---- conv plan (built once per layer; holds TMA descriptors + launch geometry) -------------------------------
 constexpr int kConvMaxStages = 12;
 constexpr int kConvMaxAcc = 8;
-constexpr int kConvThreads = 192;  // warp0: TMA producer, warp1: UMMA issuer, warps 2-5: epilogue
+constexpr int kConvThreads = 224;  // warp0: TMA A producer, warp1: UMMA issuer, warps 2-5: epilogue, warp6: TMA B
+constexpr int kConvMaxCout = 1024;
 
 struct ConvKParams {
   int N, Ho, Wo;
   int tiles_w, tiles_h, tiles_n, n_ntiles, total_tiles;
   int tw_log2, th_log2;  // TW*TH*TN == 128
-  int taps, kblocks, KB, BN, stages;
+  int taps, kblocks, KB, BN, stages, cout_pad;
   int c_in_off;
   int tap_dc[9], tap_dw[9], tap_d2[9], tap_dh[9];
   const float* bias;
@@ -60,6 +61,7 @@ struct ConvKParams {
   const float* head_b;
   int head_n;
   float* head_out;
+  long long* dbg;  // optional timeline buffer (CTA 0, first 64 tiles): [role 0..2][64][4] clock64 stamps
 };
 
 struct ConvPlan {
