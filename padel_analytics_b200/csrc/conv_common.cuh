@@ -1,0 +1,109 @@
+// Epilogue helpers shared by the conv kernels (per-tap conv_tc_kernel and halo conv_halo_kernel).
+#pragma once
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace pb {
+
+// bias + activation on 16 accumulator columns; `act` is CTA-uniform and each case is a straight unrolled loop so
+// the 16 independent MUFU chains interleave
+__device__ __forceinline__ void bias_act16(const uint32_t (&r)[16], const float* __restrict__ sbias, int act,
+                                           float (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * q);
+    v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b.x;
+    v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b.y;
+    v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
+    v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
+  }
+  if (act == PB_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
+  } else if (act == PB_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == PB_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+  }
+}
+
+struct EpiPix {
+  bool valid;
+  int n, oh, ow;
+  size_t pix;
+};
+
+// residual / fused head / store of 16 activated channels starting at output channel ch0 (c = column in the N tile)
+__device__ __forceinline__ void epilogue_store16(const ConvKParams& kp, const EpiPix& px, int ch0, int c,
+                                                 float (&v)[16], float (&hacc)[8]) {
+  if (kp.res != nullptr) {
+    const uint4* rp = reinterpret_cast<const uint4*>(kp.res + px.pix * kp.res_C + kp.res_coff + ch0);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const uint4 rv = __ldg(rp + g);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        v[8 * g + 2 * j] += f.x;
+        v[8 * g + 2 * j + 1] += f.y;
+      }
+    }
+  }
+  if (kp.head_n > 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < kp.head_n) {
+        const float4* w4 = reinterpret_cast<const float4*>(kp.head_w + (size_t)j * kp.BN + c);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; q += 2) {
+          const float4 wa = __ldg(w4 + q), wb = __ldg(w4 + q + 1);
+          s0 = fmaf(wa.x, v[4 * q], fmaf(wa.y, v[4 * q + 1], fmaf(wa.z, v[4 * q + 2], fmaf(wa.w, v[4 * q + 3], s0))));
+          s1 = fmaf(wb.x, v[4 * q + 4], fmaf(wb.y, v[4 * q + 5], fmaf(wb.z, v[4 * q + 6], fmaf(wb.w, v[4 * q + 7], s1))));
+        }
+        hacc[j] += s0 + s1;
+      }
+    }
+  }
+  if (kp.out_mode == PB_OUT_F16_NHWC || kp.out_mode == PB_OUT_F16_NHWC_UP2) {
+    uint4 pk[2];
+    __half2* h2 = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h2[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    __half* ob = reinterpret_cast<__half*>(kp.out);
+    const bool two = (kp.cout_store - ch0 >= 16);  // cout_store is a multiple of 8
+    if (kp.out_mode == PB_OUT_F16_NHWC) {
+      uint4* op = reinterpret_cast<uint4*>(ob + px.pix * kp.out_C + kp.out_coff + ch0);
+      op[0] = pk[0];
+      if (two) op[1] = pk[1];
+    } else {
+      const int Wo2 = kp.Wo * 2;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t pix2 = ((size_t)px.n * (kp.Ho * 2) + (px.oh * 2 + dy)) * Wo2 + (px.ow * 2 + dx);
+          uint4* op = reinterpret_cast<uint4*>(ob + pix2 * kp.out_C + kp.out_coff + ch0);
+          op[0] = pk[0];
+          if (two) op[1] = pk[1];
+        }
+    }
+  } else if (kp.out_mode == PB_OUT_F32_NHWC) {
+    float* op = reinterpret_cast<float*>(kp.out) + px.pix * kp.out_C + kp.out_coff + ch0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (ch0 + j < kp.cout_store) op[j] = v[j];
+  } else if (kp.out_mode == PB_OUT_F32_NCHW) {
+    float* ob = reinterpret_cast<float*>(kp.out);
+    const size_t plane = (size_t)kp.Ho * kp.Wo;
+    const size_t base = (size_t)px.n * kp.cout_store * plane + (size_t)px.oh * kp.Wo + px.ow;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (ch0 + j < kp.cout_store) ob[base + (size_t)(ch0 + j) * plane] = v[j];
+  }
+}
+
+}  // namespace pb

@@ -1,0 +1,368 @@
+// 3x3 / stride-1 conv + bias + activation as an implicit GEMM whose nine filter taps are all served from ONE
+// shared-memory halo tile per 64(32/16)-channel block.
+//
+// Why: with one TMA box per tap (conv_tc_kernel) every K-block of a small-N layer moves 16 KB of activations for
+// four UMMAs and the kernel is bound by L2->SM / TMA delivery (measured 0.35-0.43 PFLOP/s on TrackNet's N=64
+// layers).  Here the CTA tile is 16 rows x (8*S) columns of output pixels = S sub-tiles of M=128; its
+// (16+2) x (8*S+2) pixel halo is fetched by a single TMA box, and tap (r,s) of sub-tile j is just a different
+// UMMA descriptor over the same bytes:
+//     start = halo + ((r*P + 8*j + s) * row_bytes),   SBO (8-row group stride) = P * row_bytes,   P = 8*S + 2
+// (one 8-row group = 8 horizontally adjacent pixels, consecutive groups = consecutive image rows).  This relies on
+// tcgen05 applying the 128/64/32-byte swizzle XOR on absolute shared-memory address bits, which
+// scripts/exp_umma_shift.py verified on B200 (descriptor base_offset = 0 is exact for any row shift / any SBO).
+// Weights are fetched per (channel block, tap group) by a second producer warp and shared by the S sub-tile MMAs.
+//
+// Replaces the same reference layers as conv_tc.cu (TrackNet Conv2DBlock models.py:5-17; ultralytics 3x3 convs).
+#include <mutex>
+
+#include "conv_common.cuh"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace pb {
+
+constexpr int kHaloMaxA = 4;
+constexpr int kHaloMaxB = 12;
+
+struct HaloSmemTail {
+  uint64_t a_full[kHaloMaxA];
+  uint64_t a_empty[kHaloMaxA];
+  uint64_t b_full[kHaloMaxB];
+  uint64_t b_empty[kHaloMaxB];
+  uint64_t tmem_full[kConvMaxAcc];
+  uint64_t tmem_empty[kConvMaxAcc];
+  uint32_t tmem_base;
+  uint32_t pad_[3];
+  float bias[kConvMaxCout];
+};
+
+struct HaloTile {
+  int tw, th, n;
+};
+__device__ __forceinline__ HaloTile halo_decode(const ConvKParams& kp, int tile) {
+  HaloTile t;
+  t.tw = tile % kp.tiles_w;
+  const int q = tile / kp.tiles_w;
+  t.th = q % kp.tiles_h;
+  t.n = q / kp.tiles_h;
+  return t;
+}
+
+__device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+         (layout << 61);
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ ConvKParams kp) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + (size_t)kp.a_stages * kp.a_bytes;
+  HaloSmemTail* tail = reinterpret_cast<HaloSmemTail*>(b_base + (size_t)kp.b_stages * kp.b_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = kp.hs_S, P = kp.hs_P, G = kp.hs_G;
+  const uint32_t row_bytes = (uint32_t)kp.KB * 2u;
+  const int tap_groups = 9 / G;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_a);
+  if (warp == 6 && lane == 0) tma_prefetch_desc(&tmap_w);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kp.a_stages; ++i) {
+      mbar_init(&tail->a_full[i], 1);
+      mbar_init(&tail->a_empty[i], 1);
+    }
+    for (int i = 0; i < kp.b_stages; ++i) {
+      mbar_init(&tail->b_full[i], 1);
+      mbar_init(&tail->b_empty[i], 1);
+    }
+    for (int i = 0; i < kp.acc_stages; ++i) {
+      mbar_init(&tail->tmem_full[i], 1);
+      mbar_init(&tail->tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tail->tmem_base, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < kp.cout_pad; i += blockDim.x) tail->bias[i] = kp.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ===================== halo producer: one TMA box per (tile, channel block) =====================
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+        const HaloTile t = halo_decode(kp, tile);
+        for (int cb = 0; cb < kp.kblocks; ++cb) {
+          mbar_wait(&tail->a_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&tail->a_full[st], kp.halo_bytes);
+          tma_load_5d(a_base + (size_t)st * kp.a_bytes, &tmap_a, &tail->a_full[st], kp.c_in_off + cb * kp.KB,
+                      t.tw * 8 * S - 1, 0, t.th * 16 - 1, t.n);
+          if (++st == kp.a_stages) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 6) {
+    // ===================== weight producer: one TMA box per (channel block, tap group) =====================
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+        for (int cb = 0; cb < kp.kblocks; ++cb) {
+          for (int tg = 0; tg < tap_groups; ++tg) {
+            mbar_wait(&tail->b_empty[st], ph ^ 1);
+            mbar_arrive_expect_tx(&tail->b_full[st], kp.b_tx_bytes);
+            tma_load_3d(b_base + (size_t)st * kp.b_bytes, &tmap_w, &tail->b_full[st], cb * kp.KB, 0, tg * G);
+            if (++st == kp.b_stages) {
+              st = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    if (lane == 0) {
+      int ast = 0, bst = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_ph = 0;
+      const int ksteps = kp.KB / 16;
+      const uint32_t sbo = (uint32_t)P * row_bytes;
+      const uint32_t tap_b_bytes = (uint32_t)kp.BN * row_bytes;
+      for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tail->tmem_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * S * kp.acc_cols);
+        for (int cb = 0; cb < kp.kblocks; ++cb) {
+          mbar_wait(&tail->a_full[ast], aph);
+          tc_fence_after();
+          const uint32_t halo = smem_u32(a_base + (size_t)ast * kp.a_bytes);
+          for (int tg = 0; tg < tap_groups; ++tg) {
+            mbar_wait(&tail->b_full[bst], bph);
+            tc_fence_after();
+            const uint32_t bsm = smem_u32(b_base + (size_t)bst * kp.b_bytes);
+            for (int ti = 0; ti < G; ++ti) {
+              const int tap = tg * G + ti;
+              const int r = tap / 3, s = tap - 3 * r;
+              const uint64_t bdesc = umma_desc_kmajor(bsm + (uint32_t)ti * tap_b_bytes, row_bytes);
+              for (int j = 0; j < S; ++j) {
+                const uint64_t adesc = umma_desc_sbo(halo + (uint32_t)(r * P + 8 * j + s) * row_bytes, row_bytes, sbo);
+                const uint32_t dj = d0 + (uint32_t)(j * kp.acc_cols);
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k)
+                  umma_f16(dj, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kp.idesc,
+                           (uint32_t)((cb | tap | k) != 0));
+              }
+            }
+            umma_commit(&tail->b_empty[bst]);
+            if (++bst == kp.b_stages) {
+              bst = 0;
+              bph ^= 1;
+            }
+          }
+          umma_commit(&tail->a_empty[ast]);
+          if (++ast == kp.a_stages) {
+            ast = 0;
+            aph ^= 1;
+          }
+        }
+        umma_commit(&tail->tmem_full[acc]);
+        if (++acc == kp.acc_stages) {
+          acc = 0;
+          acc_ph ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: warps 2-5, S sub-tiles of 16 rows x 8 columns each =====================
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const int row = m >> 3, col = m & 7;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+      const HaloTile t = halo_decode(kp, tile);
+      mbar_wait(&tail->tmem_full[acc], acc_ph);
+      tc_fence_after();
+      for (int j = 0; j < S; ++j) {
+        EpiPix px;
+        px.n = t.n;
+        px.oh = t.th * 16 + row;
+        px.ow = t.tw * 8 * S + 8 * j + col;
+        px.valid = (px.ow < kp.Wo) && (px.oh < kp.Ho);
+        px.pix = ((size_t)px.n * kp.Ho + px.oh) * kp.Wo + px.ow;
+        const uint32_t t_addr =
+            tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * S + j) * kp.acc_cols);
+        float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < kp.BN; c += 32) {
+          uint32_t r0[16], r1[16];
+          const bool second = (c + 16 < kp.BN);
+          tmem_ld16(t_addr + (uint32_t)c, r0);
+          if (second) tmem_ld16(t_addr + (uint32_t)(c + 16), r1);
+          tmem_ld_wait();
+          if (px.valid && c < kp.cout_store) {
+            float v[16];
+            bias_act16(r0, tail->bias + c, kp.act, v);
+            epilogue_store16(kp, px, c, c, v, hacc);
+          }
+          if (second && px.valid && c + 16 < kp.cout_store) {
+            float v[16];
+            bias_act16(r1, tail->bias + c + 16, kp.act, v);
+            epilogue_store16(kp, px, c + 16, c + 16, v, hacc);
+          }
+        }
+        if (kp.head_n > 0 && px.valid) {
+          const size_t plane = (size_t)kp.Ho * kp.Wo;
+          float* ho = kp.head_out + (size_t)px.n * kp.head_n * plane + (size_t)px.oh * kp.Wo + px.ow;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < kp.head_n) ho[(size_t)q * plane] = __fdividef(1.f, 1.f + __expf(-(hacc[q] + __ldg(kp.head_b + q))));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+      if (++acc == kp.acc_stages) {
+        acc = 0;
+        acc_ph ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host: geometry + tensor maps for the halo variant. Returns 0 and sets plan->variant = 1 when applicable,
+// returns -1 (no error) when the layer should use the per-tap kernel.
+// ------------------------------------------------------------------------------------------------------------
+int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode) {
+  if (d->ksize != 3 || d->stride != 1 || d->cout_pad > 256) return -1;
+  ConvKParams& kp = plan->kp;  // common fields (epilogue, KB, kblocks, idesc, ...) already filled by the caller
+  const int BN = d->cout_pad;
+  const uint32_t row_bytes = (uint32_t)kp.KB * 2u;
+  const int acc_cols = (BN + 31) / 32 * 32;
+  const size_t budget = 196 * 1024;
+  // Choose S (sub-tiles per CTA tile: fewer halo + weight bytes per pixel) first, then G (taps per weight box:
+  // fewer TMA operations) as large as shared memory allows.
+  const uint32_t tap_bytes = (uint32_t)BN * row_bytes;
+  int bestS = 0, best_cols = 0, G = 1;
+  for (int S = 4; S >= 1; S >>= 1) {
+    if (S * acc_cols * 2 > 512) continue;  // keep >= 2 accumulator sets in TMEM
+    const uint32_t halo = 18u * (uint32_t)(8 * S + 2) * row_bytes;
+    const uint32_t a_alloc = (halo + 1023u) & ~1023u;
+    int g_fit = 0;
+    for (int g = 9; g >= 1; g = (g == 9 ? 3 : (g == 3 ? 1 : 0))) {
+      const uint32_t ba = ((uint32_t)g * tap_bytes + 1023u) & ~1023u;
+      const int min_b = g == 9 ? 2 : (g == 3 ? 3 : 4);
+      if ((size_t)2 * a_alloc + (size_t)min_b * ba <= budget) {
+        g_fit = g;
+        break;
+      }
+    }
+    if (!g_fit) continue;
+    const int cols = (d->W + 8 * S - 1) / (8 * S) * 8 * S;  // padded width actually computed
+    if (bestS == 0 || cols < best_cols) {
+      bestS = S;
+      best_cols = cols;
+      G = g_fit;
+    }
+  }
+  const uint32_t b_alloc = ((uint32_t)G * tap_bytes + 1023u) & ~1023u;
+  if (bestS == 0) return -1;
+  const int S = bestS, P = 8 * S + 2;
+  kp.hs_S = S;
+  kp.hs_P = P;
+  kp.hs_G = G;
+  kp.BN = BN;
+  kp.n_ntiles = 1;
+  kp.halo_bytes = 18u * (uint32_t)P * row_bytes;
+  kp.a_bytes = (kp.halo_bytes + 1023u) & ~1023u;
+  kp.b_tx_bytes = (uint32_t)G * tap_bytes;
+  kp.b_bytes = b_alloc;
+  kp.a_stages = 2;
+  size_t rest = budget - (size_t)2 * kp.a_bytes;
+  if (kp.kblocks > 2 && rest > (size_t)kp.a_bytes + 4 * (size_t)b_alloc) {  // a third halo buffer when K is deep
+    kp.a_stages = 3;
+    rest -= kp.a_bytes;
+  }
+  int bs = (int)(rest / b_alloc);
+  if (bs > kHaloMaxB) bs = kHaloMaxB;
+  if (bs > 9 * kp.kblocks / G * 2) bs = 9 * kp.kblocks / G * 2;
+  if (bs < 2) bs = 2;
+  kp.b_stages = bs;
+  kp.acc_cols = acc_cols;
+  kp.acc_stages = 512 / (S * acc_cols);
+  if (kp.acc_stages > kConvMaxAcc) kp.acc_stages = kConvMaxAcc;
+  kp.idesc = umma_idesc_f16(BN, 0);
+  kp.tiles_w = (kp.Wo + 8 * S - 1) / (8 * S);
+  kp.tiles_h = (kp.Ho + 15) / 16;
+  kp.tiles_n = kp.N;
+  kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
+  plan->smem_bytes = (size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes + sizeof(HaloSmemTail) + 1024;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
+  plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+  plan->variant = 1;
+
+  const CUtensorMapSwizzle swz = kp.KB == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : kp.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                               : CU_TENSOR_MAP_SWIZZLE_32B;
+  {
+    const cuuint64_t C = (cuuint64_t)d->C, W = (cuuint64_t)d->W, H = (cuuint64_t)d->H;
+    cuuint64_t dims[5] = {C, W, 1, H, (cuuint64_t)d->N};
+    cuuint64_t strides[4] = {C * 2, W * C * 2, W * C * 2, H * W * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)kp.KB, (cuuint32_t)P, 1, 18, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&plan->tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d->in), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)d->cout_pad, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * d->cout_pad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kp.KB, (cuuint32_t)BN, (cuuint32_t)G};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&plan->tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d->weight), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+  }
+  return 0;
+}
+
+int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  PB_CHECK(attr_err == cudaSuccess, "conv(halo): cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
+  conv_halo_kernel<<<plan->grid, kConvThreads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->kp);
+  PB_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace pb

@@ -14,11 +14,13 @@
 //
 // Replaces: ultralytics Conv/C2f/Bottleneck/Detect convs (3P) and TrackNet Conv2DBlock
 // (/root/reference/trackers/ball_tracker/models.py:5-17) with BN folded into weight/bias.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
 #include "internal.h"
 #include "ptx.cuh"
+#include "conv_common.cuh"
 
 namespace pb {
 
@@ -45,107 +47,6 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& kp, int tile
   c.th = t % kp.tiles_h;
   c.tn = t / kp.tiles_h;
   return c;
-}
-
-// bias + activation on 16 accumulator columns; `act` is CTA-uniform and each case is a straight unrolled loop so
-// the 16 independent MUFU chains interleave
-__device__ __forceinline__ void bias_act16(const uint32_t (&r)[16], const float* __restrict__ sbias, int act,
-                                           float (&v)[16]) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * q);
-    v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b.x;
-    v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b.y;
-    v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
-    v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
-  }
-  if (act == PB_ACT_SILU) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
-  } else if (act == PB_ACT_RELU) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-  } else if (act == PB_ACT_SIGMOID) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
-  }
-}
-
-struct EpiPix {
-  bool valid;
-  int n, oh, ow;
-  size_t pix;
-};
-
-// residual / fused head / store of 16 activated channels starting at output channel ch0 (c = column in the N tile)
-__device__ __forceinline__ void epilogue_store16(const ConvKParams& kp, const EpiPix& px, int ch0, int c,
-                                                 float (&v)[16], float (&hacc)[8]) {
-  if (kp.res != nullptr) {
-    const uint4* rp = reinterpret_cast<const uint4*>(kp.res + px.pix * kp.res_C + kp.res_coff + ch0);
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const uint4 rv = __ldg(rp + g);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h2[j]);
-        v[8 * g + 2 * j] += f.x;
-        v[8 * g + 2 * j + 1] += f.y;
-      }
-    }
-  }
-  if (kp.head_n > 0) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < kp.head_n) {
-        const float4* w4 = reinterpret_cast<const float4*>(kp.head_w + (size_t)j * kp.BN + c);
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; q += 2) {
-          const float4 wa = __ldg(w4 + q), wb = __ldg(w4 + q + 1);
-          s0 = fmaf(wa.x, v[4 * q], fmaf(wa.y, v[4 * q + 1], fmaf(wa.z, v[4 * q + 2], fmaf(wa.w, v[4 * q + 3], s0))));
-          s1 = fmaf(wb.x, v[4 * q + 4], fmaf(wb.y, v[4 * q + 5], fmaf(wb.z, v[4 * q + 6], fmaf(wb.w, v[4 * q + 7], s1))));
-        }
-        hacc[j] += s0 + s1;
-      }
-    }
-  }
-  if (kp.out_mode == PB_OUT_F16_NHWC || kp.out_mode == PB_OUT_F16_NHWC_UP2) {
-    uint4 pk[2];
-    __half2* h2 = reinterpret_cast<__half2*>(pk);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) h2[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-    __half* ob = reinterpret_cast<__half*>(kp.out);
-    const bool two = (kp.cout_store - ch0 >= 16);  // cout_store is a multiple of 8
-    if (kp.out_mode == PB_OUT_F16_NHWC) {
-      uint4* op = reinterpret_cast<uint4*>(ob + px.pix * kp.out_C + kp.out_coff + ch0);
-      op[0] = pk[0];
-      if (two) op[1] = pk[1];
-    } else {
-      const int Wo2 = kp.Wo * 2;
-#pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const size_t pix2 = ((size_t)px.n * (kp.Ho * 2) + (px.oh * 2 + dy)) * Wo2 + (px.ow * 2 + dx);
-          uint4* op = reinterpret_cast<uint4*>(ob + pix2 * kp.out_C + kp.out_coff + ch0);
-          op[0] = pk[0];
-          if (two) op[1] = pk[1];
-        }
-    }
-  } else if (kp.out_mode == PB_OUT_F32_NHWC) {
-    float* op = reinterpret_cast<float*>(kp.out) + px.pix * kp.out_C + kp.out_coff + ch0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (ch0 + j < kp.cout_store) op[j] = v[j];
-  } else if (kp.out_mode == PB_OUT_F32_NCHW) {
-    float* ob = reinterpret_cast<float*>(kp.out);
-    const size_t plane = (size_t)kp.Ho * kp.Wo;
-    const size_t base = (size_t)px.n * kp.cout_store * plane + (size_t)px.oh * kp.Wo + px.ow;
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (ch0 + j < kp.cout_store) ob[base + (size_t)(ch0 + j) * plane] = v[j];
-  }
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -358,10 +259,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
@@ -432,6 +329,33 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   kp.taps = d->ksize * d->ksize;
   kp.KB = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0 ? 32 : 16);
   kp.kblocks = d->cin / kp.KB;
+  kp.c_in_off = d->c_in_off;
+  kp.bias = d->bias;
+  kp.act = d->act;
+  kp.res = reinterpret_cast<const __half*>(d->res);
+  kp.res_C = d->res_C;
+  kp.res_coff = d->res_coff;
+  kp.out = d->out;
+  kp.out_C = d->out_C;
+  kp.out_coff = d->out_coff;
+  kp.out_mode = d->out_mode;
+  kp.cout_store = d->cout_store;
+  kp.head_w = d->head_weight;
+  kp.head_b = d->head_bias;
+  kp.head_n = d->head_n;
+  kp.head_out = d->head_out;
+  kp.dbg = g_conv_dbg;
+  plan->variant = 0;
+  {
+    // halo variant for 3x3/s1 layers: default on for cout <= 128 (the layers the per-tap kernel leaves
+    // L2/TMA-bound); PADEL_B200_CONV_HALO=0 disables it, =1 forces it wherever it applies
+    const char* e = getenv("PADEL_B200_CONV_HALO");
+    const int mode = e ? atoi(e) : 2;
+    if (mode == 1 || (mode == 2 && d->cout_pad <= 128)) {
+      const int rc = conv_halo_setup(d, plan, encode);
+      if (rc >= 0) return rc;
+    }
+  }
   // N tile: largest multiple-of-16 divisor of cout_pad that is <= 256
   int nn = (d->cout_pad + 255) / 256;
   while (d->cout_pad % nn != 0 || (d->cout_pad / nn) % 16 != 0) ++nn;
@@ -462,7 +386,6 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n * kp.n_ntiles;
   (void)ilog2;
 
-  kp.c_in_off = d->c_in_off;
   for (int r = 0; r < d->ksize; ++r)
     for (int q = 0; q < d->ksize; ++q) {
       const int t = r * d->ksize + q;
@@ -480,21 +403,6 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
         kp.tap_d2[t] = (dy != 0) ? 1 : 0;
       }
     }
-  kp.bias = d->bias;
-  kp.act = d->act;
-  kp.res = reinterpret_cast<const __half*>(d->res);
-  kp.res_C = d->res_C;
-  kp.res_coff = d->res_coff;
-  kp.out = d->out;
-  kp.out_C = d->out_C;
-  kp.out_coff = d->out_coff;
-  kp.out_mode = d->out_mode;
-  kp.cout_store = d->cout_store;
-  kp.head_w = d->head_weight;
-  kp.head_b = d->head_bias;
-  kp.head_n = d->head_n;
-  kp.head_out = d->head_out;
-  kp.dbg = g_conv_dbg;
   // TMEM accumulator ring: as many buffers as fit (<= 8) so short-K tiles are not bound by the
   // MMA -> epilogue -> MMA hand-shake latency
   kp.acc_cols = (kp.BN + 31) / 32 * 32;
@@ -551,6 +459,7 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
 }
 
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
+  if (plan->variant == 1) return conv_halo_launch(plan, stream);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {

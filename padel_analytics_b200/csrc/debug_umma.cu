@@ -8,11 +8,11 @@ namespace pb {
 
 __global__ void __launch_bounds__(128, 1)
 debug_umma_shift_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                        float* __restrict__ D, int shift_rows, int sbo_bytes, int base_off_mode) {
+                        float* __restrict__ D, int shift_rows, int sbo_bytes, int base_off_mode, int row_bytes) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* a_s = smem;               // 192 rows x 128 B
-  uint8_t* b_s = smem + 192 * 128;   // 64 rows x 128 B
+  uint8_t* a_s = smem;               // 192 rows x row_bytes
+  uint8_t* b_s = smem + 192 * 128;   // 64 rows x row_bytes
   uint64_t* bar = reinterpret_cast<uint64_t*>(b_s + 64 * 128);
   uint64_t* bar2 = bar + 1;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 2);
@@ -31,7 +31,7 @@ debug_umma_shift_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   tc_fence_after();
   const uint32_t tmem = *tptr;
   if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar, 192 * 128 + 64 * 128);
+    mbar_arrive_expect_tx(bar, 192 * row_bytes + 64 * row_bytes);
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
             "r"(smem_u32(a_s)), "l"(reinterpret_cast<uint64_t>(&tmap_a)), "r"(smem_u32(bar)), "r"(0), "r"(0)
@@ -42,13 +42,13 @@ debug_umma_shift_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         : "memory");
     mbar_wait(bar, 0);
     tc_fence_after();
-    const uint32_t a_addr = smem_u32(a_s) + (uint32_t)shift_rows * 128u;
+    const uint32_t a_addr = smem_u32(a_s) + (uint32_t)shift_rows * (uint32_t)row_bytes;
     uint64_t adesc = (uint64_t)((a_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-                     (1ull << 46) | (2ull << 61);
+                     (1ull << 46) | ((row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull)) << 61);
     if (base_off_mode == 1) adesc |= (uint64_t)((a_addr >> 7) & 7) << 49;
-    const uint64_t bdesc = umma_desc_kmajor(smem_u32(b_s), 128);
+    const uint64_t bdesc = umma_desc_kmajor(smem_u32(b_s), (uint32_t)row_bytes);
     const uint32_t idesc = umma_idesc_f16(64, 0);
-    for (int k = 0; k < 4; ++k) umma_f16(tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0);
+    for (int k = 0; k < row_bytes / 32; ++k) umma_f16(tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0);
     umma_commit(bar2);
   }
   mbar_wait(bar2, 0);
@@ -72,34 +72,36 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 
 extern "C" int pb_debug_umma_shift(const void* A /*half [192][64]*/, const void* B /*half [64][64]*/,
                                    float* D /*[128][64]*/, int shift_rows, int sbo_bytes, int base_off_mode,
-                                   void* stream) {
+                                   int row_bytes, void* stream) {
   using namespace pb;
   void* p = nullptr;
   cudaDriverEntryPointQueryResult q;
   PB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
   EncodeTiledFn2 enc = reinterpret_cast<EncodeTiledFn2>(p);
   CUtensorMap ma, mb;
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   cuuint32_t es[2] = {1, 1};
   {
-    cuuint64_t dims[2] = {64, 192};
-    cuuint64_t str[1] = {128};
-    cuuint32_t box[2] = {64, 192};
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes / 2, 192};
+    cuuint64_t str[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)row_bytes / 2, 192};
     PB_CHECK(enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(A), dims, str, box, es,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, "encode A failed");
   }
   {
-    cuuint64_t dims[2] = {64, 64};
-    cuuint64_t str[1] = {128};
-    cuuint32_t box[2] = {64, 64};
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes / 2, 64};
+    cuuint64_t str[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)row_bytes / 2, 64};
     PB_CHECK(enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(B), dims, str, box, es,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, "encode B failed");
   }
   const size_t smem = 192 * 128 + 64 * 128 + 64 + 1024;
   PB_CUDA(cudaFuncSetAttribute(debug_umma_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   debug_umma_shift_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(ma, mb, D, shift_rows, sbo_bytes,
-                                                                              base_off_mode);
+                                                                              base_off_mode, row_bytes);
   PB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -61,6 +61,8 @@ struct ConvKParams {
   const float* head_b;
   int head_n;
   float* head_out;
+  int hs_S, hs_P, hs_G, a_stages, b_stages;  // halo variant: sub-tiles, halo pitch (px), taps per weight box, rings
+  uint32_t halo_bytes;
   long long* dbg;  // optional timeline buffer (CTA 0, first 64 tiles): [role 0..2][64][4] clock64 stamps
 };
 
@@ -71,8 +73,14 @@ struct ConvPlan {
   CUtensorMap tmap_w;
   int grid;
   size_t smem_bytes;
+  int variant;  // 0 = per-tap boxes (conv_tc_kernel), 1 = shared halo tile (conv_halo_kernel)
 };
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);  // -1: not applicable
+int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream);
 int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan);
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
 int conv_reference_launch(const pb_conv_desc* d, cudaStream_t stream);

@@ -101,8 +101,27 @@ def test_reference_kernel_matches_torch(case):
     assert bad == 0.0, f"reference kernel: {bad*100:.3f}% elements out of tolerance (max err {mx})"
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
-def test_tcgen05_conv_matches_torch(case):
+HALO_CASES = [
+    dict(N=1, H=32, W=64, cin=64, cout=64, k=3, s=1, act=L.ACT_RELU),
+    dict(N=2, H=36, W=52, cin=64, cout=64, k=3, s=1, act=L.ACT_RELU),            # ragged: H % 16, W % 8 != 0
+    dict(N=2, H=20, W=12, cin=128, cout=128, k=3, s=1, act=L.ACT_SILU),
+    dict(N=1, H=48, W=80, cin=192, cout=64, k=3, s=1, act=L.ACT_RELU),           # 3 channel blocks
+    dict(N=2, H=24, W=40, cin=48, cout=80, k=3, s=1, act=L.ACT_SILU),            # KB=16 rows (32B swizzle)
+    dict(N=2, H=24, W=40, cin=32, cout=32, k=3, s=1, act=L.ACT_SILU, residual=True, c_total=96, c_in_off=32,
+         out_coff=64, out_extra=32),                                             # KB=32 (64B swizzle) + slices
+    dict(N=3, H=17, W=9, cin=16, cout=16, k=3, s=1, act=L.ACT_SILU),
+    dict(N=1, H=16, W=32, cin=64, cout=128, k=3, s=1, act=L.ACT_RELU, out_mode=L.OUT_F16_NHWC_UP2),
+    dict(N=1, H=36, W=64, cin=256, cout=256, k=3, s=1, act=L.ACT_RELU),          # S=1, two accumulator sets
+    dict(N=2, H=16, W=32, cin=64, cout=27, k=3, s=1, act=L.ACT_NONE, out_mode=L.OUT_F32_NHWC, out_coff=64,
+         out_extra=3),
+]
+
+
+@pytest.mark.parametrize("halo", [0, 1], ids=["pertap", "halo"])
+@pytest.mark.parametrize("case", CASES + HALO_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_tcgen05_conv_matches_torch(case, halo, monkeypatch):
+    """Both tensor-core variants (per-tap TMA boxes / shared halo tile; the latter only applies to 3x3 s1)."""
+    monkeypatch.setenv("PADEL_B200_CONV_HALO", str(halo))
     bad, mx = run_case(**case)
     assert bad == 0.0, f"tcgen05 kernel: {bad*100:.3f}% elements out of tolerance (max err {mx})"
 
