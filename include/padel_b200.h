@@ -122,13 +122,13 @@ int pb_tracknet_pack_windows(const uint8_t* frames, int ring, int first_slot, co
 
 /* ---- YOLOv8 head decode + NMS (ultralytics Detect/Pose decode, ops.non_max_suppression) --- */
 typedef struct pb_yolo_level {
-  const float* feat; /* float NHWC (B, h, w, fC): [0,64) DFL logits, [64,64+nc) class logits, [64+nc, +nk) kpts */
+  const float* feat; /* float NHWC (B, h, w, fC): [0,64) DFL logits, [cls_off,+nc) class logits, [kpt_off,+nk) kpts */
   int h, w, stride;
 } pb_yolo_level;
 /* cand: float (B, cap, 6+nk) rows = x1,y1,x2,y2,conf,cls,kpts(raw decoded, network px); cand_count: int (B).
  * Candidates are those with max class score > conf and (class_filter<0 or best class == class_filter).         */
-int pb_yolo_decode(const pb_yolo_level* levels, int nlevels, int B, int fC, int nc, int nk, int kdim, float conf,
-                   int class_filter, float* cand, int* cand_anchor, int* cand_count, int cap, void* stream);
+int pb_yolo_decode(const pb_yolo_level* levels, int nlevels, int B, int fC, int nc, int nk, int kdim, int cls_off,
+                   int kpt_off, float conf, int class_filter, float* cand, int* cand_anchor, int* cand_count, int cap, void* stream);
 /* Per-image: sort by (conf desc, anchor asc), greedy NMS with IoU > iou suppression on class-offset boxes
  * (offset 7680*cls), keep first max_det. out: float (B, max_det, 6+nk); out_count int (B).                      */
 int pb_yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count, int B, int cap, int rowlen,

@@ -53,43 +53,44 @@ __global__ void upsample2_kernel(const __half* __restrict__ in, int N, int H, in
   }
 }
 
-// SPPF: y1 = mp5(x'), y2 = mp5(y1), y3 = mp5(y2) with MaxPool2d(5,1,2) (-inf padding) == windows 5, 9, 13 of x'.
+// SPPF: y1 = mp5(x'), y2 = mp5(y1), y3 = mp5(y2) with MaxPool2d(5,1,2) (-inf padding).
 // buf is the concat buffer (N,H,W,C=4c): slice 0 holds x', slices 1..3 are written.
-__global__ void sppf_pool_kernel(__half* __restrict__ buf, int N, int H, int W, int C, int cg) {
-  const long total = (long)N * H * W * cg;
+// One CTA per (image, 8-channel group): the (H,W) plane of 16-byte vectors lives in shared memory and the three
+// chained pools run as separable row/column passes (2x5 reads per pool instead of 169 reads per pixel).
+__global__ void __launch_bounds__(256) sppf_pool_kernel(__half* __restrict__ buf, int N, int H, int W, int C,
+                                                        int cg) {
+  extern __shared__ uint4 sppf_smem[];
+  uint4* cur = sppf_smem;           // H*W
+  uint4* tmp = sppf_smem + H * W;   // H*W (row-pass result)
+  const int g = blockIdx.x % cg;
+  const int n = blockIdx.x / cg;
   const int c = cg * 8;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    long p = i / cg;
-    const int w = (int)(p % W);
-    const int h = (int)((p / W) % H);
-    const int n = (int)(p / ((long)W * H));
-    const __half ninf = __ushort_as_half((unsigned short)0xFC00);
-    uint4 m5, m9, m13;
-    {
-      __half2 t = __halves2half2(ninf, ninf);
-      uint4 init;
-      __half2* z = reinterpret_cast<__half2*>(&init);
-      z[0] = z[1] = z[2] = z[3] = t;
-      m5 = m9 = m13 = init;
-    }
-    for (int dy = -6; dy <= 6; ++dy) {
-      const int y = h + dy;
-      if (y < 0 || y >= H) continue;
-      for (int dx = -6; dx <= 6; ++dx) {
-        const int x = w + dx;
-        if (x < 0 || x >= W) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(buf + (((size_t)n * H + y) * W + x) * C + g * 8);
-        m13 = hmax8(m13, v);
-        const int ay = dy < 0 ? -dy : dy, ax = dx < 0 ? -dx : dx;
-        if (ay <= 4 && ax <= 4) m9 = hmax8(m9, v);
-        if (ay <= 2 && ax <= 2) m5 = hmax8(m5, v);
+  const int HW = H * W;
+  __half* base = buf + (size_t)n * HW * C + g * 8;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) cur[i] = *reinterpret_cast<const uint4*>(base + (size_t)i * C);
+  __syncthreads();
+  for (int pass = 1; pass <= 3; ++pass) {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {  // horizontal max over [x-2, x+2]
+      const int x = i % W, y = i / W;
+      uint4 m = cur[i];
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int xx = x + dx;
+        if (dx != 0 && xx >= 0 && xx < W) m = hmax8(m, cur[y * W + xx]);
       }
+      tmp[i] = m;
     }
-    __half* o = buf + (((size_t)n * H + h) * W + w) * C + g * 8;
-    *reinterpret_cast<uint4*>(o + c) = m5;
-    *reinterpret_cast<uint4*>(o + 2 * c) = m9;
-    *reinterpret_cast<uint4*>(o + 3 * c) = m13;
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {  // vertical max over [y-2, y+2]
+      const int x = i % W, y = i / W;
+      uint4 m = tmp[i];
+      for (int dy = -2; dy <= 2; ++dy) {
+        const int yy = y + dy;
+        if (dy != 0 && yy >= 0 && yy < H) m = hmax8(m, tmp[yy * W + x]);
+      }
+      cur[i] = m;
+      *reinterpret_cast<uint4*>(base + (size_t)i * C + pass * c) = m;
+    }
+    __syncthreads();
   }
 }
 
@@ -128,8 +129,14 @@ int launch_upsample2(const void* in, int N, int H, int W, int C, int c_off, int 
 
 int launch_sppf_pool(void* buf, int N, int H, int W, int C, int c, cudaStream_t s) {
   PB_CHECK(c % 8 == 0 && C >= 4 * c && C % 8 == 0, "sppf: bad channel layout");
-  const long total = (long)N * H * W * (c / 8);
-  sppf_pool_kernel<<<grid_for(total, 128), 128, 0, s>>>(reinterpret_cast<__half*>(buf), N, H, W, C, c / 8);
+  const size_t smem = (size_t)2 * H * W * sizeof(uint4);
+  PB_CHECK(smem <= 200 * 1024, "sppf: %dx%d plane does not fit in shared memory", H, W);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    PB_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  sppf_pool_kernel<<<N * (c / 8), 256, smem, s>>>(reinterpret_cast<__half*>(buf), N, H, W, C, c / 8);
   PB_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -93,9 +93,22 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& kp, const Ep
     }
   } else if (kp.out_mode == PB_OUT_F32_NHWC) {
     float* op = reinterpret_cast<float*>(kp.out) + px.pix * kp.out_C + kp.out_coff + ch0;
+    if (((kp.out_C | kp.out_coff) & 3) == 0) {  // 16-byte aligned rows: vector stores for the full groups
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (ch0 + j < kp.cout_store) op[j] = v[j];
+      for (int q = 0; q < 4; ++q) {
+        if (ch0 + 4 * q + 4 <= kp.cout_store) {
+          *reinterpret_cast<float4*>(op + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 4 * q; j < 4 * q + 4; ++j)
+            if (ch0 + j < kp.cout_store) op[j] = v[j];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (ch0 + j < kp.cout_store) op[j] = v[j];
+    }
   } else if (kp.out_mode == PB_OUT_F32_NCHW) {
     float* ob = reinterpret_cast<float*>(kp.out);
     const size_t plane = (size_t)kp.Ho * kp.Wo;

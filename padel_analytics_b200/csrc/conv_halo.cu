@@ -103,8 +103,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
         const HaloTile t = halo_decode(kp, tile);
+        const int seq = (tile - blockIdx.x) / gridDim.x;
+        const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
+        if (dbg) kp.dbg[(0 * 64 + seq) * 4 + 0] = clock64();
         for (int cb = 0; cb < kp.kblocks; ++cb) {
           mbar_wait(&tail->a_empty[st], ph ^ 1);
+          if (dbg && cb == 0) kp.dbg[(0 * 64 + seq) * 4 + 1] = clock64();
           mbar_arrive_expect_tx(&tail->a_full[st], kp.halo_bytes);
           tma_load_5d(a_base + (size_t)st * kp.a_bytes, &tmap_a, &tail->a_full[st], kp.c_in_off + cb * kp.KB,
                       t.tw * 8 * S - 1, 0, t.th * 16 - 1, t.n);
@@ -145,12 +149,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t sbo = (uint32_t)P * row_bytes;
       const uint32_t tap_b_bytes = (uint32_t)kp.BN * row_bytes;
       for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+        const int seq = (tile - blockIdx.x) / gridDim.x;
+        const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
+        if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 0] = clock64();
         mbar_wait(&tail->tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
+        if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 1] = clock64();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * S * kp.acc_cols);
         for (int cb = 0; cb < kp.kblocks; ++cb) {
           mbar_wait(&tail->a_full[ast], aph);
           tc_fence_after();
+          if (dbg && cb == 0) kp.dbg[(1 * 64 + seq) * 4 + 2] = clock64();
           const uint32_t halo = smem_u32(a_base + (size_t)ast * kp.a_bytes);
           for (int tg = 0; tg < tap_groups; ++tg) {
             mbar_wait(&tail->b_full[bst], bph);
@@ -182,6 +191,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         umma_commit(&tail->tmem_full[acc]);
+        if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 3] = clock64();
         if (++acc == kp.acc_stages) {
           acc = 0;
           acc_ph ^= 1;
@@ -190,16 +200,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: warps 2-5, S sub-tiles of 16 rows x 8 columns each =====================
+    // ===== epilogue: two groups of 4 warps (2-5, 7-10) alternating tiles; S sub-tiles of 16 rows x 8 columns each
+    const int egroup = warp >= 7 ? 1 : 0;
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const int row = m >> 3, col = m & 7;
-    int acc = 0;
-    uint32_t acc_ph = 0;
-    for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + egroup * gridDim.x; tile < kp.total_tiles; tile += 2 * gridDim.x) {
       const HaloTile t = halo_decode(kp, tile);
+      const int seq = (tile - blockIdx.x) / gridDim.x;
+      const int acc = seq % kp.acc_stages;
+      const uint32_t acc_ph = (uint32_t)(seq / kp.acc_stages) & 1u;
+      const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64 && (threadIdx.x == 64 || threadIdx.x == 224);
+      if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 0] = clock64();
       mbar_wait(&tail->tmem_full[acc], acc_ph);
       tc_fence_after();
+      if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 1] = clock64();
       for (int j = 0; j < S; ++j) {
         EpiPix px;
         px.n = t.n;
@@ -238,10 +253,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
-      if (++acc == kp.acc_stages) {
-        acc = 0;
-        acc_ph ^= 1;
-      }
+      if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 2] = clock64();
     }
   }
 

@@ -185,16 +185,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ============================== epilogue (warps 2-5, one TMEM lane quarter each) ==========================
+    // ============ epilogue: two groups of 4 warps (2-5 and 7-10), alternating tiles; one TMEM lane quarter per warp
+    const int egroup = warp >= 7 ? 1 : 0;
     const int quarter = warp & 3;
     const int p = quarter * 32 + lane;  // row of the M=128 tile handled by this thread
     const int TWm = (1 << kp.tw_log2) - 1, THm = (1 << kp.th_log2) - 1;
     const int tw_i = p & TWm;
     const int th_i = (p >> kp.tw_log2) & THm;
     const int tn_i = p >> (kp.tw_log2 + kp.th_log2);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + egroup * gridDim.x; tile < kp.total_tiles; tile += 2 * gridDim.x) {
+      const int seq = (tile - blockIdx.x) / gridDim.x;  // per-CTA tile sequence number
+      const int acc = seq % kp.acc_stages;
+      const uint32_t acc_phase = (uint32_t)(seq / kp.acc_stages) & 1u;
       const TileCoord tc = decode_tile(kp, tile);
       EpiPix px;
       px.ow = (tc.tw << kp.tw_log2) + tw_i;
@@ -202,8 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       px.n = tc.tn * (128 >> (kp.tw_log2 + kp.th_log2)) + tn_i;
       px.valid = (px.ow < kp.Wo) && (px.oh < kp.Ho) && (px.n < kp.N);
       px.pix = ((size_t)px.n * kp.Ho + px.oh) * kp.Wo + px.ow;
-      const int seq = (tile - blockIdx.x) / gridDim.x;
-      const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64 && threadIdx.x == 64;
+      const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64 && (threadIdx.x == 64 || threadIdx.x == 224);
       if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 0] = clock64();
       mbar_wait(&tail->tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -240,10 +241,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (j < kp.head_n) ho[(size_t)j * plane] = __fdividef(1.f, 1.f + __expf(-(hacc[j] + __ldg(kp.head_b + j))));
-      }
-      if (++acc == kp.acc_stages) {
-        acc = 0;
-        acc_phase ^= 1;
       }
     }
   }

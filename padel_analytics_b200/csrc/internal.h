@@ -38,7 +38,7 @@ int num_sms();
 // ---- conv plan (built once per layer; holds TMA descriptors + launch geometry) -------------------------------
 constexpr int kConvMaxStages = 12;
 constexpr int kConvMaxAcc = 8;
-constexpr int kConvThreads = 224;  // warp0: TMA A producer, warp1: UMMA issuer, warps 2-5: epilogue, warp6: TMA B
+constexpr int kConvThreads = 352;  // w0: TMA-A, w1: UMMA issuer, w2-5: epilogue group 0, w6: TMA-B, w7-10: epilogue group 1
 constexpr int kConvMaxCout = 1024;
 
 struct ConvKParams {

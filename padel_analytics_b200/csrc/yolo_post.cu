@@ -12,7 +12,7 @@ constexpr int kMaxLevels = 4;
 struct DecodeParams {
   const float* feat[kMaxLevels];
   int h[kMaxLevels], w[kMaxLevels], stride[kMaxLevels], start[kMaxLevels + 1];
-  int nlevels, B, fC, nc, nk, kdim, class_filter, cap, rowlen;
+  int nlevels, B, fC, nc, nk, kdim, class_filter, cap, rowlen, cls_off, kpt_off;
   float conf;
 };
 
@@ -32,10 +32,11 @@ __global__ void yolo_decode_kernel(DecodeParams p, float* __restrict__ cand, int
     const int gx = la % p.w[l], gy = la / p.w[l];
     const float* f = p.feat[l] + ((size_t)b * p.h[l] * p.w[l] + la) * p.fC;
     // best class (sigmoid is monotonic: argmax on logits, first max wins like torch.max)
-    float best = f[64];
+    const float* fc = f + p.cls_off;
+    float best = fc[0];
     int bj = 0;
     for (int j = 1; j < p.nc; ++j) {
-      const float v = f[64 + j];
+      const float v = fc[j];
       if (v > best) {
         best = v;
         bj = j;
@@ -77,7 +78,7 @@ __global__ void yolo_decode_kernel(DecodeParams p, float* __restrict__ cand, int
     row[3] = cy + hh;
     row[4] = score;
     row[5] = (float)bj;
-    const float* kp = f + 64 + p.nc;
+    const float* kp = f + p.kpt_off;
     const int K = p.kdim > 0 ? p.nk / p.kdim : 0;
     for (int k = 0; k < K; ++k) {
       const float vx = kp[k * p.kdim], vy = kp[k * p.kdim + 1];
@@ -182,16 +183,19 @@ using namespace pb;
 
 extern "C" {
 
-int pb_yolo_decode(const pb_yolo_level* levels, int nlevels, int B, int fC, int nc, int nk, int kdim, float conf,
-                   int class_filter, float* cand, int* cand_anchor, int* cand_count, int cap, void* stream) {
+int pb_yolo_decode(const pb_yolo_level* levels, int nlevels, int B, int fC, int nc, int nk, int kdim, int cls_off,
+                   int kpt_off, float conf, int class_filter, float* cand, int* cand_anchor, int* cand_count, int cap, void* stream) {
   PB_CHECK(levels && cand && cand_anchor && cand_count, "yolo_decode: null pointer");
   PB_CHECK(nlevels >= 1 && nlevels <= kMaxLevels, "yolo_decode: 1..%d levels", kMaxLevels);
   PB_CHECK(nc >= 1 && fC >= 64 + nc + nk, "yolo_decode: feature width %d < 64+nc+nk", fC);
+  PB_CHECK(cls_off >= 64 && cls_off + nc <= fC && (nk == 0 || (kpt_off >= 64 && kpt_off + nk <= fC)),
+           "yolo_decode: bad cls/kpt offsets");
   PB_CHECK(kdim == 0 || kdim == 2 || kdim == 3, "yolo_decode: kdim must be 0, 2 or 3");
   PB_CHECK(kdim == 0 ? nk == 0 : nk % kdim == 0, "yolo_decode: nk not a multiple of kdim");
   DecodeParams p;
   p.nlevels = nlevels; p.B = B; p.fC = fC; p.nc = nc; p.nk = nk; p.kdim = kdim;
   p.class_filter = class_filter; p.cap = cap; p.rowlen = 6 + nk; p.conf = conf;
+  p.cls_off = cls_off; p.kpt_off = kpt_off;
   p.start[0] = 0;
   for (int l = 0; l < nlevels; ++l) {
     p.feat[l] = levels[l].feat; p.h[l] = levels[l].h; p.w[l] = levels[l].w; p.stride[l] = levels[l].stride;

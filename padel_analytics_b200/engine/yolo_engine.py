@@ -194,11 +194,14 @@ class YoloEngine:
         c2f(cat20, 0, c3 + c4, 21, o5, 0, False)
 
         # heads: per level box / cls (/ kpt) branches -> one fp32 NHWC map (B,h,w,64+nc+nk)
-        fC = 64 + self.nc + self.nk
+        # head map layout: [box 0:64 | kpt 64:64+nk | cls ...], 16-byte aligned slices so the epilogue stores float4
+        kpt_off = 64
+        cls_off = 64 + (self.nk + 3) // 4 * 4
+        fC = (cls_off + self.nc + 3) // 4 * 4
         feats, levels = [], []
-        branches = [("cv2", 64, 0), ("cv3", self.nc, 64)]
+        branches = [("cv2", 64, 0), ("cv3", self.nc, cls_off)]
         if self.nk:
-            branches.append(("cv4", self.nk, 64 + self.nc))
+            branches.append(("cv4", self.nk, kpt_off))
         for l, (f, cf, st) in enumerate(((o3, c2, 8), (o4, c3, 16), (o5, c4, 32))):
             _, h, w_, _ = f.shape
             feat = buf(h, w_, fC, torch.float32)
@@ -217,7 +220,8 @@ class YoloEngine:
         for l, (feat, h, w_, st) in enumerate(levels):
             lv[l].feat, lv[l].h, lv[l].w, lv[l].stride = feat.data_ptr(), h, w_, st
         rowlen = 6 + self.nk
-        st = dict(prog=P, bufs=bufs, x0=x0, levels=lv, fC=fC, rowlen=rowlen, Hn=Hn, Wn=Wn,
+        st = dict(prog=P, bufs=bufs, x0=x0, levels=lv, fC=fC, rowlen=rowlen, Hn=Hn, Wn=Wn, cls_off=cls_off,
+                  kpt_off=kpt_off,
                   cand=torch.zeros((B, self.CAND_CAP, rowlen), dtype=torch.float32, device=dev),
                   cand_anchor=torch.zeros((B, self.CAND_CAP), dtype=torch.int32, device=dev),
                   cand_count=torch.zeros((B,), dtype=torch.int32, device=dev),
@@ -299,7 +303,8 @@ class YoloEngine:
             raise L.PbError("YoloEngine: only a single-class filter (or None) is supported")
         cf = -1 if classes is None else int(classes[0])
         kdim = self.kpt_shape[1] if self.kpt_shape else 0
-        L.check(lib.pb_yolo_decode(st["levels"], 3, self.B, st["fC"], self.nc, self.nk, kdim, float(conf), cf,
+        L.check(lib.pb_yolo_decode(st["levels"], 3, self.B, st["fC"], self.nc, self.nk, kdim, st["cls_off"],
+                                   st["kpt_off"], float(conf), cf,
                                    st["cand"].data_ptr(), st["cand_anchor"].data_ptr(), st["cand_count"].data_ptr(),
                                    self.CAND_CAP, L.stream_ptr()))
         key = ("out", max_det)

@@ -27,6 +27,9 @@ def run(N, H, W, cin, cout, k, s=1, mode=L.OUT_F16_NHWC, act=L.ACT_SILU):
     for i in list(range(0, 14)) + [30, 31, 32, 33]:
         r = lambda a: int(a) - t0
         print(f"{i:3d} | {r(t[0,i,0]):7d} {r(t[0,i,1]):7d} | {r(t[1,i,0]):7d} {r(t[1,i,1]):7d} {r(t[1,i,2]):7d} {r(t[1,i,3]):7d} | {r(t[2,i,0]):7d} {r(t[2,i,1]):7d} {r(t[2,i,2]):7d}")
-run(32, 320, 320, 32, 32, 1)
+import os
+os.environ["PADEL_B200_CONV_HALO"] = "1"
+print("halo: prod = [tile start, got a_empty] ; mma = [start, got acc, got a_full(cb0), committed] ; epi = [start, got tmem_full, done]")
 run(32, 288, 512, 64, 64, 3, act=L.ACT_RELU)
-run(8, 640, 640, 16, 16, 3, 2)
+run(32, 288, 512, 192, 64, 3, act=L.ACT_RELU)
+run(32, 160, 160, 32, 32, 3)

@@ -133,7 +133,12 @@ def test_yolo_heads_and_detections_match_oracle(kind, imgsz, prep):
     with torch.no_grad():
         raws = net.raw_heads(xin)
     for l, r in enumerate(raws):
-        got = st["feats"][l][:B].cpu().permute(0, 3, 1, 2)
+        g = st["feats"][l][:B].cpu()  # engine layout [box | kpt | cls] -> oracle layout [box | cls | kpt]
+        nc_, nk_ = eng.nc, eng.nk
+        parts = [g[..., :64], g[..., st["cls_off"]:st["cls_off"] + nc_]]
+        if nk_:
+            parts.append(g[..., st["kpt_off"]:st["kpt_off"] + nk_])
+        got = torch.cat(parts, -1).permute(0, 3, 1, 2)
         err = (got - r).abs()
         rel = err.max().item() / r.abs().max().item()
         print(kind, "level", l, "raw head max abs err", err.max().item(), "mean", err.mean().item(), "max |ref|",

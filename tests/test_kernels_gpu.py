@@ -182,7 +182,7 @@ def test_decode_nms_matches_oracle(nc, kpt):
     cand = torch.zeros((B, cap, rowlen), device=DEV)
     anchor = torch.zeros((B, cap), dtype=torch.int32, device=DEV)
     count = torch.zeros((B,), dtype=torch.int32, device=DEV)
-    L.check(L.lib().pb_yolo_decode(lv, 3, B, fC, nc, nk, kpt[1] if kpt else 0, conf, 0 if nc > 1 else -1,
+    L.check(L.lib().pb_yolo_decode(lv, 3, B, fC, nc, nk, kpt[1] if kpt else 0, 64, 64 + nc, conf, 0 if nc > 1 else -1,
                                    cand.data_ptr(), anchor.data_ptr(), count.data_ptr(), cap, L.stream_ptr()))
     out = torch.zeros((B, max_det, rowlen), device=DEV)
     ocnt = torch.zeros((B,), dtype=torch.int32, device=DEV)
