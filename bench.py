@@ -238,28 +238,25 @@ def main():
     NBUF = 3
     dev_batches = [synth.make_frames(B, H, W, start=rank * 100000 + i * B, device=dev) for i in range(NBUF)]
     host_batches = [b.cpu().pin_memory() for b in dev_batches]
-    ball_pipe = ball._pipeline(hw, med)
-    total_frames_ball = 10 ** 9  # steady state: never reaches the tail flush
+    from padel_analytics_b200.trackers.runner import FusedPass
 
-    def step(batches, i):
-        fr = batches[i % NBUF]
-        n_det = 0
-        r = trackers["players"].predict_sample(fr)
-        n_det += sum(len(p) for p in r)
-        r = trackers["pose"].predict_sample(fr)
-        n_det += sum(len(p) for p in r)
-        trackers["court"].predict_sample(fr)
-        ball_pipe.push_frames(fr)
-        nb = min(B, ball_pipe.windows_ready())
-        if nb > 0:
-            f0, bbox = ball_pipe.run_windows(nb, total_frames_ball)
-            bbox_to_xyv(bbox, (W / 512, H / 288))
-        return n_det
+    # The measured path is the fused single pass (trackers/runner.py::FusedPass): one upload per batch shared by the
+    # four trackers, device work of all four enqueued back to back, host post-processing overlapped.
+    named = {"players": trackers["players"], "pose": trackers["pose"], "court": trackers["court"], "ball": ball}
+    fused = FusedPass(named, hw, B, total_frames=10 ** 9)  # steady state: the tail flush is never reached
+    ball._pipe.push_frames(dev_batches[0][:7])  # prime the 8-frame window so every step yields B windows
 
-    ball_pipe.reset()
-    ball_pipe.push_frames(dev_batches[0][:7])  # prime the window so every step yields B windows
+    def run_steps(batches, steps):
+        nd = 0
+        for out in fused.run(batches[i % NBUF] for i in range(steps)):
+            nd += sum(len(p) for p in out["players"]) + sum(len(p) for p in out["pose"])
+        return nd
+
+    import gc
 
     def timed(batches, steps):
+        gc.collect()
+        gc.freeze()  # keep the (large, static) engine object graph out of the cyclic collector's way
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -267,9 +264,7 @@ def main():
         l0 = L.lib().pb_launch_count()
         t0 = time.perf_counter()
         e0.record()
-        nd = 0
-        for i in range(steps):
-            nd += step(batches, i)
+        nd = run_steps(batches, steps)
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -281,19 +276,17 @@ def main():
             ms, wall = t[0].item(), t[1].item() / 1e3
         return ms, wall, L.lib().pb_launch_count() - l0, nd
 
-    for i in range(args.warmup):
-        step(dev_batches, i)
+    run_steps(dev_batches, args.warmup)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_dev, wall_dev, launches, ndet = timed(dev_batches, args.steps)
-    for i in range(2):
-        step(host_batches, i)
+    run_steps(host_batches, 2)
     ms_e2e, wall_e2e, _, _ = timed(host_batches, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     frames_total = B * args.steps * world
-    value = frames_total / (max(ms_dev, 1e-9) / 1e3)
+    value = frames_total / (max(ms_dev, wall_dev * 1e3) / 1e3)
     e2e = frames_total / (max(ms_e2e, wall_e2e * 1e3) / 1e3)
 
     # roofline of the dominant kernel (conv_tc_kernel): algorithmic FLOPs of every conv launch of one step divided
@@ -340,20 +333,21 @@ def main():
         ndet = int(sum(int(g.item()) for g in gathered))
 
     if rank == 0:
-        h2d = 4 * B * H * W * 3  # each of the four trackers uploads the batch itself (like the reference's 4 decodes)
+        h2d = B * H * W * 3  # one pinned-host -> device upload per batch, shared by the four trackers
         d2h = sum(int(np.prod(st[k][2].shape)) * 4 for t in ("players", "pose", "court")
                   for st in trackers[t].model._progs.values() for k in st if isinstance(k, tuple)) + (B + 7) * 16
         print(json.dumps({
             "metric": "frames/sec through trackers.runner (all 4 trackers)", "value": round(value, 2),
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": round(max(ms_dev, wall_dev * 1e3) / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 storage, f32 accumulate", "data": "synthetic",
             "config": {"workload": f"all four trackers, synthetic {args.res} frames, batch_size={B} per GPU "
                                    f"(BASELINE.json configs[1]); YOLOv8n detect@384x640 + pose13x3@1280 + "
                                    f"court12x3@640 + TrackNet 27->8@288x512, seeded random weights",
                        "global_batch": B * world, "l2": "inputs (199 MB/batch) and activations exceed L2; no flush",
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
-                       "detections_in_timed_region": ndet},
+                       "detections_in_timed_region": ndet,
+                       "pass": "fused single pass: one upload per batch shared by the four trackers"},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(max(ms_e2e, wall_e2e * 1e3) / args.steps, 3)},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,

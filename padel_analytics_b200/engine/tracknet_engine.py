@@ -195,7 +195,7 @@ class BallPipeline:
         n = frames_bgr.shape[0]
         if n == 0:
             return
-        if frames_bgr.device != self.dev:
+        if frames_bgr.device.type != "cuda":
             self.stage[:n].copy_(frames_bgr, non_blocking=True)
             frames_bgr = self.stage[:n]
         self._resize(frames_bgr.contiguous(), n, self.small_stage, swap_rb=1)
@@ -214,6 +214,11 @@ class BallPipeline:
     def run_windows(self, nb: int, total_frames: int, want_ens: bool = False):
         """Process the next nb windows (nb <= B). Returns (first_frame, host int32 (nframes,4) bboxes) for the frames
         emitted: absolute frames [first_frame, first_frame+nframes)."""
+        return self.run_windows_async(nb, total_frames, want_ens)()
+
+    def run_windows_async(self, nb: int, total_frames: int, want_ens: bool = False):
+        """Enqueue the device work for the next nb windows; returns a callable that waits and yields
+        (first_frame, bboxes).  One call in flight."""
         eng = self.eng
         assert 0 < nb <= self.B and nb <= self.windows_ready()
         w0 = self.base + self.n_windows  # absolute window index
@@ -238,8 +243,14 @@ class BallPipeline:
         carry = eng.pred[nb:nb + 7].clone()
         eng.pred[:7].copy_(carry)
         self.n_windows += nb
-        torch.cuda.current_stream().synchronize()
-        return w0, self.bbox_host[:nframes].numpy().copy()
+        done = torch.cuda.Event()
+        done.record()
+
+        def finish():
+            done.synchronize()
+            return w0, self.bbox_host[:nframes].numpy().copy()
+
+        return finish
 
 
 def bbox_to_xyv(bbox: np.ndarray, img_scaler: tuple[float, float]):

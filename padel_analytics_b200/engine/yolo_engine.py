@@ -249,7 +249,7 @@ class YoloEngine:
             raise L.PbError("frames must be uint8 (n,H,W,3)")
         if t.shape[0] > self.B:
             raise L.PbError(f"batch {t.shape[0]} exceeds engine max_batch {self.B}")
-        if t.device != self.device:
+        if t.device.type != "cuda":
             n = t.shape[0]
             if self._stage is None or self._stage.shape[1:] != t.shape[1:]:
                 self._stage = torch.empty((self.B,) + tuple(t.shape[1:]), dtype=torch.uint8, device=self.device)
@@ -297,6 +297,10 @@ class YoloEngine:
     # forward + decode + NMS + host epilogue
     # ------------------------------------------------------------------------------------------------------
     def _detect(self, st, n, conf, iou, classes, max_det):
+        return self._detect_finish(self._detect_launch(st, n, conf, iou, classes, max_det))
+
+    def _detect_launch(self, st, n, conf, iou, classes, max_det):
+        """Enqueue forward + decode + NMS + the device->pinned-host copies on the current stream; no host sync."""
         lib = L.lib()
         st["prog"].run()
         if classes is not None and len(classes) != 1:
@@ -320,7 +324,13 @@ class YoloEngine:
         out_h.copy_(out, non_blocking=True)
         cnt_h[0].copy_(cnt, non_blocking=True)
         cnt_h[1].copy_(st["cand_count"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        done = torch.cuda.Event()
+        done.record()
+        return (done, out_h, cnt_h, n)
+
+    def _detect_finish(self, handle):
+        done, out_h, cnt_h, n = handle
+        done.synchronize()
         if int(cnt_h[1][:n].max()) > self.CAND_CAP:
             raise L.PbError(f"YoloEngine: {int(cnt_h[1][:n].max())} candidates exceed CAND_CAP={self.CAND_CAP}")
         return out_h.numpy(), cnt_h[0].numpy()
@@ -399,3 +409,24 @@ class YoloEngine:
             raise L.PbError(f"unknown prep {prep!r}")
         rows, counts = self._detect(st, n, conf, iou, classes, max_det)
         return self._results(rows, counts, n, (st["Hn"], st["Wn"]), orig)
+
+    @torch.no_grad()
+    def predict_frames_async(self, frames, prep: str, conf, iou, imgsz, classes=None, max_det=300):
+        """predict_frames split in two: enqueue all device work now, return a callable that waits for it and builds
+        the Results (lets a caller overlap several trackers' device work with each other's host post-processing).
+        One call in flight per engine."""
+        fr = self._upload(frames)
+        n = fr.shape[0]
+        if prep == "letterbox_q1":
+            st, orig = self._letterbox(fr, imgsz, (0, 1, 2))
+        elif prep == "pil_square":
+            st, orig = self._pil_square(fr, imgsz)
+        else:
+            raise L.PbError(f"unknown prep {prep!r}")
+        handle = self._detect_launch(st, n, conf, iou, classes, max_det)
+
+        def finish():
+            rows, counts = self._detect_finish(handle)
+            return self._results(rows, counts, n, (st["Hn"], st["Wn"]), orig)
+
+        return finish

@@ -183,6 +183,45 @@ class BallTracker(Tracker):
             push(chunk)
         return out
 
+    # ---- streaming interface used by the fused single-pass runner (one batch at a time, device work asynchronous) ----
+    def stream_begin(self, frame_hw, total_frames: int, first_frame: int = 0, emit_range=None, median=None):
+        median = self.median if median is None else median
+        if median is None:
+            raise ValueError("stream_begin needs a background median (pass median= to BallTracker or here)")
+        pipe = self._pipeline(tuple(frame_hw), median)
+        pipe.reset(base=first_frame)
+        self._stream = dict(total=total_frames, emit=emit_range,
+                            scaler=(self.video_info.width / self.WIDTH, self.video_info.height / self.HEIGHT))
+        return pipe
+
+    def stream_push_async(self, frames: torch.Tensor):
+        """frames: uint8 (n,H,W,3) BGR tensor (device or pinned host), n <= batch_size.  Enqueues resize + every
+        window that became computable; returns a callable that waits and yields {frame: (x, y, vis)}."""
+        pipe, s = self._pipe, self._stream
+        pipe.push_frames(frames)
+        fins = []
+        while True:
+            nb = min(self.batch_size, pipe.windows_ready(), s["total"] - 7 - (pipe.base + pipe.n_windows))
+            if nb <= 0:
+                break
+            if fins:  # only one launch may be in flight per pipeline: resolve the previous one first
+                res = fins[-1]()
+                fins[-1] = (lambda r: (lambda: r))(res)
+            fins.append(pipe.run_windows_async(nb, s["total"]))
+
+        def finish():
+            out = {}
+            for fin in fins:
+                f0, bbox = fin()
+                xs, ys, vs = bbox_to_xyv(bbox, s["scaler"])
+                for i in range(len(xs)):
+                    n = f0 + i
+                    if s["emit"] is None or s["emit"][0] <= n < s["emit"][1]:
+                        out[n] = (xs[i], ys[i], vs[i])
+            return out
+
+        return finish
+
     def predict_frames(self, frame_generator: Iterable[np.ndarray], total_frames: int, **kwargs) -> list[Ball]:
         xyv = self.track_xyv(frame_generator, total_frames)
         balls = []

@@ -109,6 +109,11 @@ class KeypointsTracker(Tracker):
         return self.model.predict_frames(sample, "pil_square", conf=self.CONF, iou=self.IOU,
                                          imgsz=self.TRAIN_IMAGE_SIZE, classes=None, max_det=self.NUMBER_KEYPOINTS)
 
+    def detect_sample_async(self, sample):
+        return self.model.predict_frames_async(sample, "pil_square", conf=self.CONF, iou=self.IOU,
+                                               imgsz=self.TRAIN_IMAGE_SIZE, classes=None,
+                                               max_det=self.NUMBER_KEYPOINTS)
+
     def postprocess(self, results, frame_hw) -> list[Keypoints]:
         """keypoints_tracker.py:229-260: the reference assumes exactly one court detection (`squeeze(0)`, q5); we take
         the highest-confidence detection (NMS output is score-sorted) and return no keypoints when there is none."""

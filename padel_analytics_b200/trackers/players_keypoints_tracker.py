@@ -137,6 +137,10 @@ class PlayerKeypointsTracker(Tracker):
         return self.model.predict_frames(sample, "pil_square", conf=self.CONF, iou=self.IOU,
                                          imgsz=self.train_image_size, classes=[0])
 
+    def detect_sample_async(self, sample):
+        return self.model.predict_frames_async(sample, "pil_square", conf=self.CONF, iou=self.IOU,
+                                               imgsz=self.train_image_size, classes=[0])
+
     def postprocess(self, results, frame_hw) -> list[PlayersKeypoints]:
         """players_keypoints_tracker.py:276-318.  The reference's `.squeeze(0)` / `len()==2` juggling crashes for
         exactly one or two detected players; here every detection count is handled uniformly."""

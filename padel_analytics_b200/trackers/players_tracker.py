@@ -134,6 +134,11 @@ class PlayerTracker(Tracker):
         return self.model.predict_frames(sample, "letterbox_q1", conf=self.CONF, iou=self.IOU, imgsz=self.IMGSZ,
                                          classes=[0])
 
+    def detect_sample_async(self, sample):
+        """Enqueue the model stage; returns a callable yielding the raw results (see YoloEngine.predict_frames_async)."""
+        return self.model.predict_frames_async(sample, "letterbox_q1", conf=self.CONF, iou=self.IOU,
+                                               imgsz=self.IMGSZ, classes=[0])
+
     def postprocess(self, results) -> list[Players]:
         """Polygon filter + ByteTrack ids (players_tracker.py:362-378); sequential, frame order matters."""
         out = []

@@ -30,6 +30,78 @@ def ball_shard_frames(total: int, start: int, end: int) -> tuple[int, int]:
     return max(0, start - 7), min(total, end + 7)
 
 
+class FusedPass:
+    """One pass over the video feeding ALL trackers from a single upload per batch (the reference decodes and uploads
+    the video once per tracker, runner.py:185-234).  Per batch: the next batch's host->device copy
+    runs on a copy stream while this batch computes; the four trackers' device work is enqueued back to back without
+    host synchronisation, and each tracker's host post-processing (ByteTrack, result objects) overlaps with the device
+    work of the trackers behind it."""
+
+    def __init__(self, trackers: dict[str, Tracker], frame_hw: tuple[int, int], batch_size: int, total_frames: int,
+                 first_frame: int = 0, emit_range: Optional[tuple[int, int]] = None):
+        self.trackers = trackers
+        self.hw = tuple(frame_hw)
+        self.B = batch_size
+        self.dev = torch.device("cuda")
+        self.copy_stream = torch.cuda.Stream()
+        self.staging = [torch.empty((batch_size,) + self.hw + (3,), dtype=torch.uint8, device=self.dev)
+                        for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        for t in trackers.values():
+            if isinstance(t, BallTracker):
+                t.stream_begin(self.hw, total_frames, first_frame, emit_range)
+
+    def _upload(self, frames, slot: int) -> torch.Tensor:
+        if not isinstance(frames, torch.Tensor):
+            frames = torch.from_numpy(np.stack(frames))
+        n = frames.shape[0]
+        if frames.device.type == "cuda":
+            return frames
+        with torch.cuda.stream(self.copy_stream):
+            self.staging[slot][:n].copy_(frames, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        return self.staging[slot][:n]
+
+    def _process(self, fr: torch.Tensor) -> dict:
+        pending = []
+        for name, t in self.trackers.items():  # enqueue everything first ...
+            if isinstance(t, BallTracker):
+                pending.append((name, t, t.stream_push_async(fr)))
+            elif getattr(t, "fixed_keypoints_detection", None) is not None:
+                pending.append((name, t, None))
+            else:
+                pending.append((name, t, t.detect_sample_async(fr)))
+        out = {}
+        for name, t, fin in pending:  # ... then finish in the same order
+            if isinstance(t, BallTracker):
+                out[name] = fin()
+            elif fin is None:
+                out[name] = [t.fixed_keypoints_detection] * fr.shape[0]
+            elif isinstance(t, PlayerTracker):
+                out[name] = t.postprocess(fin())
+            else:
+                out[name] = t.postprocess(fin(), self.hw)
+        return out
+
+    def run(self, batches: Iterable):
+        """batches: iterable of uint8 (n,H,W,3) BGR batches (pinned host tensors, device tensors or lists of frames),
+        n <= batch_size.  Yields one {tracker name: results} dict per batch."""
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        cur_dev = self._upload(cur, 0)
+        i = 0
+        while cur is not None:
+            nxt = next(it, None)
+            nxt_dev = self._upload(nxt, (i + 1) % 2) if nxt is not None else None  # overlaps with the compute below
+            if cur_dev.data_ptr() == self.staging[i % 2].data_ptr():
+                torch.cuda.current_stream().wait_event(self.ready[i % 2])
+            yield self._process(cur_dev)
+            cur, cur_dev = nxt, nxt_dev
+            i += 1
+
+
 class TrackingRunner:
     def __init__(self, trackers: dict[str, Tracker] | list[Tracker], video_path: Optional[str] = None,
                  inference_path: Optional[str] = None, start: int = 0, end: Optional[int] = None,

@@ -112,3 +112,38 @@ def test_runner_all_four_synthetic():
     assert set(timings) == {"players_tracker", "players_keypoints_tracker", "keypoints_tracker", "ball_tracker"}
     for t in trackers:
         assert len(t.results) == T
+
+
+def test_fused_pass_equals_per_tracker_passes():
+    """FusedPass (one upload per batch, all four trackers' device work enqueued together) must give exactly the
+    results of the reference-style sequential per-tracker passes."""
+    from padel_analytics_b200.trackers.runner import FusedPass
+
+    T, B = 21, 8
+    frames = synth.make_frames(T, H, W, start=11)
+    fr = [f.numpy() for f in frames]
+    med = synth.make_median(H, W).numpy()
+    poly = sv.PolygonZone(np.array([[0, 0], [W - 1, 0], [W - 1, H - 1], [0, H - 1]]), frame_resolution_wh=(W, H))
+    tr = {"players": PlayerTracker(OW.make_yolo("detect"), poly, batch_size=B),
+          "pose": PlayerKeypointsTracker(OW.make_yolo("pose13", cls_mean=-5.5), 1280, batch_size=B, load_path=None,
+                                         save_path=None),
+          "court": KeypointsTracker(OW.make_yolo("court12"), batch_size=B, model_type="yolo"),
+          "ball": BallTracker(OW.make_tracknet(), None, batch_size=B, median=med)}
+    for t in tr.values():
+        t.video_info_post_init(_vi(T))
+    seq = {}
+    for k in ("players", "pose", "court"):
+        seq[k] = [o.serialize() for o in tr[k].predict_and_update(iter(fr)).predictions]
+        tr[k].restart()
+    seq["ball"] = [(b.xy[0], b.xy[1], b.visibility) for b in tr["ball"].predict_frames(iter(fr), total_frames=T)]
+    fused = FusedPass(tr, (H, W), B, total_frames=T)
+    host = frames.pin_memory()
+    got = {k: [] for k in ("players", "pose", "court")}
+    ball = {}
+    for out in fused.run(host[i:i + B] for i in range(0, T, B)):
+        for k in got:
+            got[k] += [o.serialize() for o in out[k]]
+        ball.update(out["ball"])
+    for k in got:
+        assert json.dumps(got[k]) == json.dumps(seq[k]), k
+    assert [ball.get(n, (0.0, 0.0, 0)) for n in range(T)] == seq["ball"]
