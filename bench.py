@@ -91,6 +91,12 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of the reference's CPU path) on the host cores, bounded sample
 # ------------------------------------------------------------------------------------------------------------
+def cpu_threads() -> int:
+    """Threads given to the CPU oracle: every host core up to 64 (beyond that PyTorch's CPU convolutions on these
+    small networks get slower, not faster)."""
+    return max(1, min(os.cpu_count() or 1, 64))
+
+
 def cpu_oracle_fps(hw, n_yolo=2, n_ball=10, seed=1234):
     """All-four-trackers frames/s of the CPU oracle: N / sum_t time_t(N) measured per tracker on small samples
     (YOLO trackers: n_yolo frames; ball: n_ball frames -> n_ball-7 windows) and normalised per frame."""
@@ -102,7 +108,7 @@ def cpu_oracle_fps(hw, n_yolo=2, n_ball=10, seed=1234):
     from oracle import yolov8 as OY
     from padel_analytics_b200 import synth
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     H, W = hw
     frames = [f.numpy() for f in synth.make_frames(max(n_yolo, n_ball), H, W, seed=seed)]
     per_frame = {}
@@ -135,12 +141,12 @@ def run_reference_arm(args, rank, world):
         cpu_oracle_fps(hw, n_yolo=1, n_ball=8)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        fps, per = cpu_oracle_fps(hw)
+        fps, per = cpu_oracle_fps(hw, n_yolo=1, n_ball=8)
         vals.append(fps)
     dt = time.perf_counter() - t0
     v = statistics.median(vals)
-    cores = os.cpu_count() or 1
-    sample = "per step: 2 frames/YOLO tracker + 10 frames (3 windows) ball, per-frame times summed"
+    cores = cpu_threads()
+    sample = "per step: 1 frame per YOLO tracker + 8 frames (1 window) ball, per-frame times summed"
     print(json.dumps({
         "impl": "reference", "metric": "frames/sec through trackers.runner (all 4 trackers)", "value": v,
         "unit": "frames/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
@@ -321,7 +327,7 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         fps, per = cpu_oracle_fps(hw)
-        cpu = {"value": round(fps, 4), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": round(fps, 4), "unit": "frames/s", "cores": cpu_threads(), "kind": "port",
                "sample": "2 frames per YOLO tracker + 10 frames (3 windows) ball on the host cores, "
                          "per-frame times summed over the four trackers",
                "per_frame_s": {k: round(v, 4) for k, v in per.items()}}
