@@ -37,6 +37,8 @@ extern "C" {
 #define PB_OUT_F16_NHWC_UP2 1 /* same, each pixel replicated 2x2 into a (2Ho, 2Wo) tensor (nearest upsample)  */
 #define PB_OUT_F32_NHWC 2     /* float, channels [out_coff, out_coff+cout_store) of an NHWC float tensor       */
 #define PB_OUT_F32_NCHW 3     /* float, planar (N, cout_store, Ho, Wo)                                         */
+#define PB_IN_NHWC 0
+#define PB_IN_STEM4 1
 #define PB_OUT_NONE 4         /* nothing stored by the conv itself (only valid with a fused head)              */
 
 const char* pb_last_error(void);
@@ -47,7 +49,7 @@ long long pb_launch_count(void);
 /* ---- fused conv + bias + activation (+ residual) : implicit GEMM on tcgen05 tensor cores ------------------
  * Replaces ultralytics Conv (Conv2d+BN+SiLU, BN folded) and TrackNet Conv2DBlock (models.py:5-17).          */
 typedef struct pb_conv_desc {
-  const void* in;  /* half NHWC (N,H,W,C)                                        */
+  const void* in;  /* half NHWC (N,H,W,C); for in_layout == PB_IN_STEM4 see below */
   int N, H, W, C;  /* C = channel stride of the input tensor (multiple of 8)     */
   int c_in_off;    /* first input channel read                                   */
   int cin;         /* channels read (multiple of 16; zero-padded weights beyond the real count) */
@@ -71,6 +73,12 @@ typedef struct pb_conv_desc {
   const float* head_bias;   /* float [head_n]                   */
   int head_n;
   float* head_out;          /* float (N, head_n, Ho, Wo)        */
+  /* PB_IN_NHWC (0): as documented above.  PB_IN_STEM4 (1): the 3-channel network input stored as 4-channel fp16
+   * pixels with a one-pixel zero border, i.e. a (N, H+2, W+2, 4) tensor whose pixel (y,x) sits at [y+1][x+1]
+   * (written by pb_letterbox_u8_f16 / pb_u8_to_f16 with out_layout = 1).  Only for the 3x3 stride-2 stem conv:
+   * C = 4, cin = 16, weight = half [3 filter rows][cout_pad][16] with k = s*4 + c (s = filter column, c = channel;
+   * k >= 12 and c == 3 are zero).  One TMA box of overlapping 16-element rows serves all three filter rows.  */
+  int in_layout;
 } pb_conv_desc;
 
 /* One-shot launches (plan + run). The *_reference variant is a plain CUDA-core kernel used by tests to
@@ -102,10 +110,11 @@ int pb_program_run_range(pb_program* p, int first, int last, void* stream);
  * src: u8 (B,Hs,Ws,3). The resized area (rh,rw) is placed at (top,left) inside (Hn,Wn); everything else is 114.
  * xofs int32[rw], xcoef int32[rw][2], yofs int32[rh], ycoef int32[rh][2]: per-axis source index and 11-bit
  * coefficient pairs computed on the host exactly as cv::resize does. If rh==Hs and rw==Ws the copy is verbatim.
- * (c0,c1,c2): source channel feeding network channel 0,1,2.                                                    */
+ * (c0,c1,c2): source channel feeding network channel 0,1,2.  out_layout 0: dst = half (B,Hn,Wn,16);
+ * out_layout 1 (PB_IN_STEM4): dst = half (B,Hn+2,Wn+2,4), interior written, the zero border left untouched.      */
 int pb_letterbox_u8_f16(const uint8_t* src, int B, int Hs, int Ws, void* dst, int Hn, int Wn, int rh, int rw,
                         int top, int left, const int32_t* xofs, const int32_t* xcoef, const int32_t* yofs,
-                        const int32_t* ycoef, int c0, int c1, int c2, void* stream);
+                        const int32_t* ycoef, int c0, int c1, int c2, int out_layout, void* stream);
 /* Pillow Image.resize (BICUBIC, reducing_gap=None) two-pass fixed-point resample, bit-exact.
  * Coefficients are computed on the host exactly as Pillow does (precompute_coeffs) and passed in:
  *   bounds_*: int32 [out][2] = (xmin, xsize); kk_*: int32 [out][ksize] (22-bit fixed point).
@@ -114,7 +123,8 @@ int pb_pil_resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* tmp, ui
                      const int32_t* bounds_h, const int32_t* kk_h, int ksize_h, const int32_t* bounds_v,
                      const int32_t* kk_v, int ksize_v, int swap_rb, void* stream);
 /* u8 (B,H,W,3) -> half NHWC (B,H,W,16): dst[...,k] = src[..., ck]/255 for k<3, 0 otherwise */
-int pb_u8_to_f16_nhwc16(const uint8_t* src, int B, int H, int W, void* dst, int c0, int c1, int c2, void* stream);
+int pb_u8_to_f16_nhwc16(const uint8_t* src, int B, int H, int W, void* dst, int c0, int c1, int c2, int out_layout,
+                        void* stream);
 /* TrackNet window assembly (iterable.py:167-199): frames u8 ring (T,H,W,3) RGB, median u8 (H,W,3) RGB ->
  * x half NHWC (B,H,W,32): channels [med(3), f[first+b+0](3) ... f[first+b+7](3), 0 x5], value/255.              */
 int pb_tracknet_pack_windows(const uint8_t* frames, int ring, int first_slot, const uint8_t* median, int B, int H,

@@ -26,6 +26,7 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p), ("out_C", C.c_int), ("out_coff", C.c_int), ("out_mode", C.c_int),
         ("cout_store", C.c_int),
         ("head_weight", C.c_void_p), ("head_bias", C.c_void_p), ("head_n", C.c_int), ("head_out", C.c_void_p),
+        ("in_layout", C.c_int),
     ]
 
 
@@ -35,6 +36,7 @@ class YoloLevel(C.Structure):
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_SIGMOID = 0, 1, 2, 3
 OUT_F16_NHWC, OUT_F16_NHWC_UP2, OUT_F32_NHWC, OUT_F32_NCHW, OUT_NONE = 0, 1, 2, 3, 4
+IN_NHWC, IN_STEM4 = 0, 1
 
 # name -> (restype, argtypes); must list every symbol of include/padel_b200.h (tests check this)
 _i, _p, _f = C.c_int, C.c_void_p, C.c_float
@@ -53,9 +55,9 @@ SIGNATURES = {
     "pb_program_num_ops": (_i, [_p]),
     "pb_program_run": (_i, [_p, _p]),
     "pb_program_run_range": (_i, [_p, _i, _i, _p]),
-    "pb_letterbox_u8_f16": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "pb_letterbox_u8_f16": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "pb_pil_resize_u8": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _i, _i, _p]),
-    "pb_u8_to_f16_nhwc16": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p]),
+    "pb_u8_to_f16_nhwc16": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p]),
     "pb_tracknet_pack_windows": (_i, [_p, _i, _i, _p, _i, _i, _i, _p, _p]),
     "pb_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _i, _p]),
     "pb_yolo_nms": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p, _p]),

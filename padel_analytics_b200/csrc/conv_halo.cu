@@ -65,9 +65,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int S = kp.hs_S, P = kp.hs_P, G = kp.hs_G;
+  const int S = kp.hs_S, G = kp.hs_G;
   const uint32_t row_bytes = (uint32_t)kp.KB * 2u;
-  const int tap_groups = 9 / G;
+  const int tap_groups = kp.hs_ntaps / G;
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_a);
   if (warp == 6 && lane == 0) tma_prefetch_desc(&tmap_w);
@@ -111,7 +111,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (dbg && cb == 0) kp.dbg[(0 * 64 + seq) * 4 + 1] = clock64();
           mbar_arrive_expect_tx(&tail->a_full[st], kp.halo_bytes);
           tma_load_5d(a_base + (size_t)st * kp.a_bytes, &tmap_a, &tail->a_full[st], kp.c_in_off + cb * kp.KB,
-                      t.tw * 8 * S - 1, 0, t.th * 16 - 1, t.n);
+                      t.tw * 8 * S + kp.hs_x0, 0, t.th * 16 + kp.hs_y0, t.n);
           if (++st == kp.a_stages) {
             st = 0;
             ph ^= 1;
@@ -146,7 +146,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int ast = 0, bst = 0, acc = 0;
       uint32_t aph = 0, bph = 0, acc_ph = 0;
       const int ksteps = kp.KB / 16;
-      const uint32_t sbo = (uint32_t)P * row_bytes;
+      const uint32_t sbo = (uint32_t)kp.hs_sbo_rows * row_bytes;
       const uint32_t tap_b_bytes = (uint32_t)kp.BN * row_bytes;
       for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
         const int seq = (tile - blockIdx.x) / gridDim.x;
@@ -167,10 +167,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t bsm = smem_u32(b_base + (size_t)bst * kp.b_bytes);
             for (int ti = 0; ti < G; ++ti) {
               const int tap = tg * G + ti;
-              const int r = tap / 3, s = tap - 3 * r;
+              const uint32_t toff = (uint32_t)kp.hs_tap_off[tap];
               const uint64_t bdesc = umma_desc_kmajor(bsm + (uint32_t)ti * tap_b_bytes, row_bytes);
               for (int j = 0; j < S; ++j) {
-                const uint64_t adesc = umma_desc_sbo(halo + (uint32_t)(r * P + 8 * j + s) * row_bytes, row_bytes, sbo);
+                const uint64_t adesc = umma_desc_sbo(halo + (toff + 8u * (uint32_t)j) * row_bytes, row_bytes, sbo);
                 const uint32_t dj = d0 + (uint32_t)(j * kp.acc_cols);
 #pragma unroll 4
                 for (int k = 0; k < ksteps; ++k)
@@ -269,6 +269,76 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // host: geometry + tensor maps for the halo variant. Returns 0 and sets plan->variant = 1 when applicable,
 // returns -1 (no error) when the layer should use the per-tap kernel.
 // ------------------------------------------------------------------------------------------------------------
+// Stem (PB_IN_STEM4): 3x3 stride-2 conv over the padded 4-channel input. One TMA box of overlapping 16-element rows
+// (4 pixels x 4 channels, consecutive rows 2 pixels apart) holds, for a tile of 16 x 8S outputs, the three filter
+// rows r = 0..2 as [oh][r][ow] rows of 32 bytes; filter row r of sub-tile j starts at row (r*8S + 8j), 8-row groups
+// (consecutive oh) are 3*8S rows apart.  K = 16 per filter row (12 real), 3 UMMAs per sub-tile.
+int conv_stem_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode) {
+  PB_CHECK(d->ksize == 3 && d->stride == 2 && d->C == 4 && d->cin == 16 && d->c_in_off == 0,
+           "conv(stem): needs ksize 3, stride 2, C = 4, cin = 16");
+  PB_CHECK(d->cout_pad <= 128, "conv(stem): cout_pad %d > 128", d->cout_pad);
+  ConvKParams& kp = plan->kp;
+  const int BN = d->cout_pad;
+  const int acc_cols = (BN + 31) / 32 * 32;
+  int S = 4;
+  while (S > 1 && (S * acc_cols * 2 > 512)) S >>= 1;
+  kp.KB = 16;
+  kp.kblocks = 1;
+  kp.taps = 3;
+  kp.hs_S = S;
+  kp.hs_P = 8 * S;
+  kp.hs_G = 3;
+  kp.hs_ntaps = 3;
+  kp.hs_sbo_rows = 3 * 8 * S;
+  kp.hs_x0 = 0;
+  kp.hs_y0 = 0;
+  for (int r = 0; r < 3; ++r) kp.hs_tap_off[r] = r * 8 * S;
+  kp.BN = BN;
+  kp.n_ntiles = 1;
+  kp.halo_bytes = 16u * 3u * (uint32_t)(8 * S) * 32u;
+  kp.a_bytes = (kp.halo_bytes + 1023u) & ~1023u;
+  kp.b_tx_bytes = 3u * (uint32_t)BN * 32u;
+  kp.b_bytes = (kp.b_tx_bytes + 1023u) & ~1023u;
+  kp.a_stages = 4;
+  kp.b_stages = 4;
+  kp.acc_cols = acc_cols;
+  kp.acc_stages = 512 / (S * acc_cols);
+  if (kp.acc_stages > kConvMaxAcc) kp.acc_stages = kConvMaxAcc;
+  kp.idesc = umma_idesc_f16(BN, 0);
+  kp.tiles_w = (kp.Wo + 8 * S - 1) / (8 * S);
+  kp.tiles_h = (kp.Ho + 15) / 16;
+  kp.tiles_n = kp.N;
+  kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
+  plan->smem_bytes = (size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes + sizeof(HaloSmemTail) + 1024;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
+  plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+  plan->variant = 1;
+  {
+    // overlapping-row view of the padded (N, H+2, W+2, 4) tensor: element (k, ow, r, oh, n) =
+    //   base + n*(H+2)*(W+2)*8 + (2*oh + r)*(W+2)*8 + (2*ow)*8 + 2*k  -> pixels 2ow-1 .. 2ow+2 of image row 2oh+r-1
+    const cuuint64_t Wp = (cuuint64_t)d->W + 2, Hp = (cuuint64_t)d->H + 2;
+    cuuint64_t dims[5] = {16, (cuuint64_t)d->W / 2, 3, (cuuint64_t)d->H / 2, (cuuint64_t)d->N};
+    cuuint64_t strides[4] = {16, Wp * 8, 2 * Wp * 8, Hp * Wp * 8};
+    cuuint32_t box[5] = {16, (cuuint32_t)(8 * S), 3, 16, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&plan->tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d->in), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "conv(stem): cuTensorMapEncodeTiled(A, overlapping rows) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {16, (cuuint64_t)d->cout_pad, 3};
+    cuuint64_t strides[2] = {32, (cuuint64_t)d->cout_pad * 32};
+    cuuint32_t box[3] = {16, (cuuint32_t)BN, 3};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&plan->tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d->weight), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "conv(stem): cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+  }
+  return 0;
+}
+
 int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode) {
   if (d->ksize != 3 || d->stride != 1 || d->cout_pad > 256) return -1;
   ConvKParams& kp = plan->kp;  // common fields (epilogue, KB, kblocks, idesc, ...) already filled by the caller
@@ -307,6 +377,12 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.hs_S = S;
   kp.hs_P = P;
   kp.hs_G = G;
+  kp.hs_ntaps = 9;
+  kp.hs_sbo_rows = P;
+  kp.hs_x0 = -1;
+  kp.hs_y0 = -1;
+  for (int r = 0; r < 3; ++r)
+    for (int q = 0; q < 3; ++q) kp.hs_tap_off[r * 3 + q] = r * P + q;
   kp.BN = BN;
   kp.n_ntiles = 1;
   kp.halo_bytes = 18u * (uint32_t)P * row_bytes;

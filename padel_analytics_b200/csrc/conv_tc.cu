@@ -280,13 +280,16 @@ extern "C" void pb_debug_conv_timeline(long long* buf) { g_conv_dbg = buf; }
 
 int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   PB_CHECK(d && plan, "conv: null argument");
+  PB_CHECK(d->in_layout == PB_IN_NHWC || d->in_layout == PB_IN_STEM4, "conv: bad in_layout");
+  const bool stem = d->in_layout == PB_IN_STEM4;
   PB_CHECK(d->ksize == 1 || d->ksize == 3, "conv: ksize %d unsupported", d->ksize);
   PB_CHECK(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
   PB_CHECK(!(d->stride == 2 && d->ksize == 1), "conv: 1x1 stride-2 unsupported");
   PB_CHECK(d->cin > 0 && d->cin % 16 == 0, "conv: cin %d must be a positive multiple of 16", d->cin);
   PB_CHECK(d->cout_pad <= kConvMaxCout, "conv: cout_pad %d > %d", d->cout_pad, kConvMaxCout);
   PB_CHECK(d->cout_pad > 0 && d->cout_pad % 16 == 0, "conv: cout_pad %d must be a multiple of 16", d->cout_pad);
-  PB_CHECK(d->C % 8 == 0 && d->c_in_off >= 0 && d->c_in_off + d->cin <= d->C, "conv: bad input channel slice");
+  PB_CHECK(stem || (d->C % 8 == 0 && d->c_in_off >= 0 && d->c_in_off + d->cin <= d->C),
+           "conv: bad input channel slice");
   PB_CHECK(d->c_in_off % 8 == 0, "conv: c_in_off must be a multiple of 8");
   PB_CHECK((reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0 &&
@@ -343,6 +346,7 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   kp.head_out = d->head_out;
   kp.dbg = g_conv_dbg;
   plan->variant = 0;
+  if (stem) return conv_stem_setup(d, plan, encode);
   {
     // halo variant for 3x3/s1 layers: default on for cout <= 128 (the layers the per-tap kernel leaves
     // L2/TMA-bound); PADEL_B200_CONV_HALO=0 disables it, =1 forces it wherever it applies
@@ -489,6 +493,12 @@ __global__ void conv_reference_kernel(pb_conv_desc d, int Ho, int Wo) {
       for (int q = 0; q < d.ksize; ++q) {
         const int ih = oh * d.stride + r - pad, iw = ow * d.stride + q - pad;
         if (ih < 0 || ih >= d.H || iw < 0 || iw >= d.W) continue;
+        if (d.in_layout == PB_IN_STEM4) {  // padded 4-channel pixels; weight [r][cout][s*4 + c]
+          const __half* ip = in + (((size_t)n * (d.H + 2) + ih + 1) * (d.W + 2) + iw + 1) * 4;
+          const __half* wp = w + ((size_t)r * d.cout_pad + co) * 16 + q * 4;
+          for (int c = 0; c < 3; ++c) acc += __half2float(ip[c]) * __half2float(wp[c]);
+          continue;
+        }
         const __half* ip = in + (((size_t)n * d.H + ih) * d.W + iw) * d.C + d.c_in_off;
         const __half* wp = w + ((size_t)(r * d.ksize + q) * d.cout_pad + co) * d.cin;
         for (int c = 0; c < d.cin; ++c) acc += __half2float(ip[c]) * __half2float(wp[c]);

@@ -63,6 +63,8 @@ struct ConvKParams {
   float* head_out;
   int hs_S, hs_P, hs_G, a_stages, b_stages;  // halo variant: sub-tiles, halo pitch (px), taps per weight box, rings
   uint32_t halo_bytes;
+  int hs_ntaps, hs_sbo_rows, hs_x0, hs_y0, hs_tile_h;  // taps served from the halo, 8-row group stride (rows), box origin offsets
+  int hs_tap_off[9];                                   // smem row offset of each tap's first pixel
   long long* dbg;  // optional timeline buffer (CTA 0, first 64 tiles): [role 0..2][64][4] clock64 stamps
 };
 
@@ -80,6 +82,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);  // -1: not applicable
+int conv_stem_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);
 int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream);
 int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan);
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);

@@ -22,7 +22,7 @@ __device__ __forceinline__ uint4 pack_px16_first(float a, float b, float c) {
 __global__ void letterbox_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws, __half* __restrict__ dst,
                                  int Hn, int Wn, int rh, int rw, int top, int left, const int* __restrict__ xofs,
                                  const int* __restrict__ xcoef, const int* __restrict__ yofs,
-                                 const int* __restrict__ ycoef, int c0, int c1, int c2) {
+                                 const int* __restrict__ ycoef, int c0, int c1, int c2, int out_layout) {
   const long total = (long)B * Hn * Wn;
   const bool identity = (rh == Hs && rw == Ws);
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -55,9 +55,15 @@ __global__ void letterbox_kernel(const uint8_t* __restrict__ src, int B, int Hs,
       }
     }
     const float inv = 1.f / 255.f;
-    uint4* o = reinterpret_cast<uint4*>(dst + (size_t)i * 16);
-    o[0] = pack_px16_first(px[c0] * inv, px[c1] * inv, px[c2] * inv);
-    o[1] = make_uint4(0, 0, 0, 0);
+    if (out_layout == 0) {
+      uint4* o = reinterpret_cast<uint4*>(dst + (size_t)i * 16);
+      o[0] = pack_px16_first(px[c0] * inv, px[c1] * inv, px[c2] * inv);
+      o[1] = make_uint4(0, 0, 0, 0);
+    } else {  // PB_IN_STEM4: (B, Hn+2, Wn+2, 4), interior only
+      const uint4 v = pack_px16_first(px[c0] * inv, px[c1] * inv, px[c2] * inv);
+      *reinterpret_cast<uint2*>(dst + (((size_t)b * (Hn + 2) + (y + 1)) * (Wn + 2) + (x + 1)) * 4) =
+          make_uint2(v.x, v.y);
+    }
   }
 }
 
@@ -108,13 +114,22 @@ __global__ void pil_vertical_kernel(const uint8_t* __restrict__ tmp, int B, int 
 }
 
 __global__ void u8_to_f16_nhwc16_kernel(const uint8_t* __restrict__ src, long npix, __half* __restrict__ dst, int c0,
-                                        int c1, int c2) {
+                                        int c1, int c2, int out_layout, int H, int W) {
   const float inv = 1.f / 255.f;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
     const uint8_t* p = src + i * 3;
-    uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
-    o[0] = pack_px16_first(p[c0] * inv, p[c1] * inv, p[c2] * inv);
-    o[1] = make_uint4(0, 0, 0, 0);
+    const uint4 v = pack_px16_first(p[c0] * inv, p[c1] * inv, p[c2] * inv);
+    if (out_layout == 0) {
+      uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
+      o[0] = v;
+      o[1] = make_uint4(0, 0, 0, 0);
+    } else {  // PB_IN_STEM4
+      const int x = (int)(i % W);
+      const long q = i / W;
+      const int y = (int)(q % H);
+      const long b = q / H;
+      *reinterpret_cast<uint2*>(dst + ((b * (H + 2) + (y + 1)) * (W + 2) + (x + 1)) * 4) = make_uint2(v.x, v.y);
+    }
   }
 }
 
@@ -166,14 +181,15 @@ extern "C" {
 
 int pb_letterbox_u8_f16(const uint8_t* src, int B, int Hs, int Ws, void* dst, int Hn, int Wn, int rh, int rw,
                         int top, int left, const int32_t* xofs, const int32_t* xcoef, const int32_t* yofs,
-                        const int32_t* ycoef, int c0, int c1, int c2, void* stream) {
+                        const int32_t* ycoef, int c0, int c1, int c2, int out_layout, void* stream) {
   PB_CHECK(src && dst, "letterbox: null pointer");
+  PB_CHECK(out_layout == 0 || out_layout == 1, "letterbox: bad out_layout");
   PB_CHECK((rh == Hs && rw == Ws) || (xofs && xcoef && yofs && ycoef), "letterbox: missing tables");
   PB_CHECK(top >= 0 && left >= 0 && top + rh <= Hn && left + rw <= Wn, "letterbox: bad geometry");
   const long total = (long)B * Hn * Wn;
   letterbox_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, B, Hs, Ws, reinterpret_cast<__half*>(dst), Hn, Wn, rh, rw, top, left, xofs, xcoef, yofs, ycoef, c0, c1,
-      c2);
+      c2, out_layout);
   PB_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -194,11 +210,13 @@ int pb_pil_resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* tmp, ui
   return 0;
 }
 
-int pb_u8_to_f16_nhwc16(const uint8_t* src, int B, int H, int W, void* dst, int c0, int c1, int c2, void* stream) {
+int pb_u8_to_f16_nhwc16(const uint8_t* src, int B, int H, int W, void* dst, int c0, int c1, int c2, int out_layout,
+                        void* stream) {
   PB_CHECK(src && dst, "u8_to_f16: null pointer");
+  PB_CHECK(out_layout == 0 || out_layout == 1, "u8_to_f16: bad out_layout");
   const long npix = (long)B * H * W;
   u8_to_f16_nhwc16_kernel<<<grid_for(npix, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, npix, reinterpret_cast<__half*>(dst), c0, c1, c2);
+      src, npix, reinterpret_cast<__half*>(dst), c0, c1, c2, out_layout, H, W);
   PB_CUDA(cudaGetLastError());
   count_launch();
   return 0;

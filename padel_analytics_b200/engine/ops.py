@@ -75,6 +75,38 @@ def make_conv_desc(x: torch.Tensor, c_in_off: int, cin: int, w: torch.Tensor, b:
     return d
 
 
+def pack_stem_weight(w: torch.Tensor, b: torch.Tensor | None, cout_pad: int, device):
+    """(Cout,3,3,3) fp32 stem weights -> half [3 filter rows][cout_pad][16] with k = s*4 + c (PB_IN_STEM4), + bias."""
+    cout = w.shape[0]
+    assert tuple(w.shape[1:]) == (3, 3, 3)
+    wp = torch.zeros(3, cout_pad, 16, dtype=torch.float32)
+    for s in range(3):
+        for c in range(3):
+            wp[:, :cout, s * 4 + c] = w[:, c, :, s].detach().float().T  # [r][cout]
+    bp = torch.zeros(cout_pad, dtype=torch.float32)
+    if b is not None:
+        bp[:cout] = b.detach().float()
+    return wp.to(torch.float16).contiguous().to(device), bp.contiguous().to(device)
+
+
+def make_stem_desc(x_padded: torch.Tensor, w: torch.Tensor, b: torch.Tensor, act: int, out: torch.Tensor,
+                   out_coff: int = 0) -> L.ConvDesc:
+    """Stem conv (3x3, stride 2) over the padded 4-channel input (N, H+2, W+2, 4)."""
+    N, Hp, Wp, C4 = x_padded.shape
+    assert C4 == 4 and w.shape[0] == 3 and w.shape[2] == 16
+    d = L.ConvDesc()
+    d.in_ = x_padded.data_ptr()
+    d.N, d.H, d.W, d.C = N, Hp - 2, Wp - 2, 4
+    d.c_in_off, d.cin = 0, 16
+    d.weight, d.bias = w.data_ptr(), b.data_ptr()
+    d.cout_pad, d.ksize, d.stride, d.act = w.shape[1], 3, 2, act
+    d.res, d.res_C, d.res_coff = None, 0, 0
+    d.out, d.out_C, d.out_coff, d.out_mode = out.data_ptr(), out.shape[-1], out_coff, L.OUT_F16_NHWC
+    d.cout_store = w.shape[1]
+    d.in_layout = L.IN_STEM4
+    return d
+
+
 def conv2d(desc: L.ConvDesc, reference: bool = False) -> None:
     fn = L.lib().pb_conv2d_reference if reference else L.lib().pb_conv2d
     L.check(fn(C.byref(desc), L.stream_ptr()))

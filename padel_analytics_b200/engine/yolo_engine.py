@@ -160,7 +160,10 @@ class YoloEngine:
                 raise L.PbError(f"YoloEngine: channel width {c} is not a multiple of 16")
         H2, W2, H4, W4, H8, W8 = Hn // 2, Wn // 2, Hn // 4, Wn // 4, Hn // 8, Wn // 8
         H16, W16, H32, W32 = Hn // 16, Wn // 16, Hn // 32, Wn // 32
-        x0 = buf(Hn, Wn, 16)
+        # network input: 4-channel fp16 pixels with a one-pixel zero border (PB_IN_STEM4), written by the
+        # pre-processing kernels; the border is never touched after this zero fill
+        x0 = torch.zeros((B, Hn + 2, Wn + 2, 4), dtype=torch.float16, device=dev)
+        bufs.append(x0)
         b0, b1, b2 = buf(H2, W2, c0), buf(H4, W4, c1), buf(H4, W4, c1)
         b3 = buf(H8, W8, c2)
         cat14 = buf(H8, W8, c3 + c2)  # [up(12) c3 | P3 c2]
@@ -172,7 +175,10 @@ class YoloEngine:
         cat17 = buf(H16, W16, c2 + c3)  # [conv16 c2 | h4 c3]
         o3, o4, o5 = buf(H8, W8, c2), buf(H16, W16, c3), buf(H32, W32, c4)
 
-        conv(x0, 0, 16, "model.0", b0, 0, 3, 2)
+        w0, bias0 = _fold(sd, "model.0")
+        if "stem" not in self._packed:
+            self._packed["stem"] = ops.pack_stem_weight(w0, bias0, ops.pad16(c0), dev)
+        P.conv(ops.make_stem_desc(x0, *self._packed["stem"], SILU, b0), cin_real=3, cout_real=c0)
         conv(b0, 0, c0, "model.1", b1, 0, 3, 2)
         c2f(b1, 0, c1, 2, b2, 0, True)
         conv(b2, 0, c1, "model.3", b3, 0, 3, 2)
@@ -269,7 +275,7 @@ class YoloEngine:
         xo, xc, yo, yc = self._tables[key]
         L.check(L.lib().pb_letterbox_u8_f16(frames_dev.data_ptr(), n, Hs, Ws, st["x0"].data_ptr(), g["Hn"], g["Wn"],
                                             g["rh"], g["rw"], g["top"], g["left"], xo.data_ptr(), xc.data_ptr(),
-                                            yo.data_ptr(), yc.data_ptr(), chan_map[0], chan_map[1], chan_map[2],
+                                            yo.data_ptr(), yc.data_ptr(), chan_map[0], chan_map[1], chan_map[2], 1,
                                             L.stream_ptr()))
         return st, (Hs, Ws)
 
@@ -289,7 +295,7 @@ class YoloEngine:
         L.check(L.lib().pb_pil_resize_u8(frames_dev.data_ptr(), n, Hs, Ws, t["tmp"].data_ptr(), t["dst"].data_ptr(),
                                          size, size, t["bh"].data_ptr(), t["kh"].data_ptr(), t["ksh"],
                                          t["bv"].data_ptr(), t["kv"].data_ptr(), t["ksv"], 1, L.stream_ptr()))
-        L.check(L.lib().pb_u8_to_f16_nhwc16(t["dst"].data_ptr(), n, size, size, st["x0"].data_ptr(), 0, 1, 2,
+        L.check(L.lib().pb_u8_to_f16_nhwc16(t["dst"].data_ptr(), n, size, size, st["x0"].data_ptr(), 0, 1, 2, 1,
                                             L.stream_ptr()))
         return st, (size, size)
 

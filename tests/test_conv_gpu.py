@@ -144,3 +144,25 @@ def test_fused_1x1_head_matches_torch():
     y = torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), b, padding=1))
     exp = torch.sigmoid(F.conv2d(y, hw.view(8, cout, 1, 1), hb))
     assert (out.cpu() - exp).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 96, 16), (1, 384, 640, 16), (3, 40, 72, 48)])
+def test_stem_conv_padded4_layout(shape):
+    """3x3/s2 stem conv reading the padded 4-channel input (PB_IN_STEM4) through one overlapping-row TMA box."""
+    N, H, W, cout = shape
+    g = torch.Generator().manual_seed(9)
+    img = torch.rand(N, H, W, 3, generator=g).half()
+    xp = torch.zeros(N, H + 2, W + 2, 4, dtype=torch.float16)
+    xp[:, 1:-1, 1:-1, :3] = img
+    w = torch.randn(cout, 3, 3, 3, generator=g) / 27 ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    wp, bp = ops.pack_stem_weight(w, b, ops.pad16(cout), "cuda")
+    y = F.silu(F.conv2d(img.float().permute(0, 3, 1, 2), w.half().float(), b, stride=2, padding=1))
+    for reference in (True, False):
+        out = torch.full((N, H // 2, W // 2, ops.pad16(cout)), 7.0, dtype=torch.float16, device="cuda")
+        d = ops.make_stem_desc(xp.cuda(), wp, bp, L.ACT_SILU, out)
+        ops.conv2d(d, reference=reference)
+        torch.cuda.synchronize()
+        got = out.cpu().float()[..., :cout].permute(0, 3, 1, 2)
+        err = (got - y).abs()
+        assert (err > 2e-3 + 2e-3 * y.abs()).float().mean().item() == 0.0, (reference, err.max().item())

@@ -125,7 +125,8 @@ def test_yolo_heads_and_detections_match_oracle(kind, imgsz, prep):
     exp = yolo.predict(sample, conf=conf, iou=0.7, imgsz=imgsz, classes=classes, max_det=max_det)
     # 1) network input identical (bit-exact preprocessing)
     st = next(iter(eng._progs.values()))
-    x0 = st["x0"][:B, ..., :3].cpu().float().permute(0, 3, 1, 2)
+    x0 = st["x0"][:B, 1:-1, 1:-1, :3].cpu().float().permute(0, 3, 1, 2)
+    assert float(st["x0"][:B, 0].abs().max()) == 0.0 and float(st["x0"][:B, :, 0].abs().max()) == 0.0  # zero border
     xin = yolo.last_preprocessed
     assert x0.shape == xin.shape
     assert (x0 - xin).abs().max().item() < 6e-4

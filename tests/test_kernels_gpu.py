@@ -35,7 +35,11 @@ def test_letterbox_bit_exact(hw):
     dst = torch.zeros((2, g["Hn"], g["Wn"], 16), dtype=torch.float16, device=DEV)
     L.check(L.lib().pb_letterbox_u8_f16(src.data_ptr(), 2, hw[0], hw[1], dst.data_ptr(), g["Hn"], g["Wn"], g["rh"],
                                         g["rw"], g["top"], g["left"], xo.data_ptr(), xc.data_ptr(), yo.data_ptr(),
-                                        yc.data_ptr(), 2, 1, 0, L.stream_ptr()))
+                                        yc.data_ptr(), 2, 1, 0, 0, L.stream_ptr()))
+    dst4 = torch.zeros((2, g["Hn"] + 2, g["Wn"] + 2, 4), dtype=torch.float16, device=DEV)
+    L.check(L.lib().pb_letterbox_u8_f16(src.data_ptr(), 2, hw[0], hw[1], dst4.data_ptr(), g["Hn"], g["Wn"], g["rh"],
+                                        g["rw"], g["top"], g["left"], xo.data_ptr(), xc.data_ptr(), yo.data_ptr(),
+                                        yc.data_ptr(), 2, 1, 0, 1, L.stream_ptr()))
     torch.cuda.synchronize()
     for i in range(2):
         ref = OY.letterbox(fr[i], 640, auto=True)[..., ::-1]  # BGR -> RGB like the predict pipeline
@@ -44,6 +48,9 @@ def test_letterbox_bit_exact(hw):
         assert got.shape == exp.shape
         assert torch.equal(got, exp), f"max diff {(got.float()-exp.float()).abs().max()*255:.3f} levels"
         assert torch.all(dst[i, ..., 3:] == 0)
+        assert torch.equal(dst4[i, 1:-1, 1:-1, :3].cpu(), exp)  # PB_IN_STEM4 layout: same values, zero border
+        assert float(dst4[i, 0].abs().max()) == 0 and float(dst4[i, :, -1].abs().max()) == 0
+        assert float(dst4[i, ..., 3].abs().max()) == 0
 
 
 @pytest.mark.parametrize("size", [(512, 288), (1280, 1280), (640, 640)])
