@@ -68,48 +68,97 @@ __global__ void letterbox_kernel(const uint8_t* __restrict__ src, int B, int Hs,
 }
 
 // Pillow ImagingResampleHorizontal_8bpc / Vertical_8bpc: ss = 1<<21; ss += px*k; out = clip8(ss >> 22)
-__global__ void pil_horizontal_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws,
-                                      uint8_t* __restrict__ tmp, int Wo, const int* __restrict__ bounds,
-                                      const int* __restrict__ kk, int ksize, int swap_rb) {
-  const long total = (long)B * Hs * Wo;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int xo = (int)(i % Wo);
-    const long row = i / Wo;  // b*Hs + y
+// Horizontal: one CTA per source row; the row is staged in shared memory with 16-byte loads, every thread then
+// produces output pixels from shared memory (3 channels each).
+__global__ void __launch_bounds__(256)
+pil_horizontal_kernel(const uint8_t* __restrict__ src, int Ws, uint8_t* __restrict__ tmp, int Wo,
+                      const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, int swap_rb) {
+  extern __shared__ __align__(16) uint8_t hrow[];
+  const size_t row = blockIdx.x;  // b*Hs + y
+  const int rowbytes = Ws * 3;
+  const uint8_t* g = src + row * (size_t)rowbytes;
+  if ((rowbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    for (int i = threadIdx.x; i < rowbytes / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(hrow)[i] = __ldg(reinterpret_cast<const uint4*>(g) + i);
+  } else {
+    for (int i = threadIdx.x; i < rowbytes; i += blockDim.x) hrow[i] = g[i];
+  }
+  __syncthreads();
+  uint8_t* o = tmp + row * (size_t)Wo * 3;
+  for (int xo = threadIdx.x; xo < Wo; xo += blockDim.x) {
     const int xmin = bounds[2 * xo], xs = bounds[2 * xo + 1];
     const int* k = kk + (size_t)xo * ksize;
-    const uint8_t* p = src + ((size_t)row * Ws + xmin) * 3;
+    const uint8_t* p = hrow + xmin * 3;
     int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
     for (int x = 0; x < xs; ++x) {
-      const int kv = k[x];
+      const int kv = __ldg(k + x);
       s0 += p[3 * x + 0] * kv;
       s1 += p[3 * x + 1] * kv;
       s2 += p[3 * x + 2] * kv;
     }
-    uint8_t* o = tmp + (size_t)i * 3;
     const uint8_t v0 = (uint8_t)min(max(s0 >> 22, 0), 255);
     const uint8_t v1 = (uint8_t)min(max(s1 >> 22, 0), 255);
     const uint8_t v2 = (uint8_t)min(max(s2 >> 22, 0), 255);
-    o[0] = swap_rb ? v2 : v0;
-    o[1] = v1;
-    o[2] = swap_rb ? v0 : v2;
+    o[3 * xo + 0] = swap_rb ? v2 : v0;
+    o[3 * xo + 1] = v1;
+    o[3 * xo + 2] = swap_rb ? v0 : v2;
   }
 }
 
-__global__ void pil_vertical_kernel(const uint8_t* __restrict__ tmp, int B, int Hs, int Wo,
-                                    uint8_t* __restrict__ dst, int Ho, const int* __restrict__ bounds,
-                                    const int* __restrict__ kk, int ksize) {
-  const long total = (long)B * Ho * Wo * 3;
-  const int rowlen = Wo * 3;
+// Vertical: one thread per 4 output pixels (12 bytes = three 32-bit words per tap row).  Writes the uint8 result
+// and/or the normalised fp16 network input directly (f16_layout 0: NHWC16, 1: PB_IN_STEM4 padded 4-channel).
+__global__ void pil_vertical_kernel(const uint8_t* __restrict__ tmp, int B, int Hs, int Wo, uint8_t* __restrict__ dst,
+                                    int Ho, const int* __restrict__ bounds, const int* __restrict__ kk, int ksize,
+                                    __half* __restrict__ dst_f16, int f16_layout) {
+  const int groups = Wo / 4;  // Wo % 4 == 0 (checked on the host)
+  const long total = (long)B * Ho * groups;
+  const int rowwords = Wo * 3 / 4;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int xc = (int)(i % rowlen);
-    const int yo = (int)((i / rowlen) % Ho);
-    const int b = (int)(i / ((long)rowlen * Ho));
+    const int gidx = (int)(i % groups);
+    const int yo = (int)((i / groups) % Ho);
+    const int b = (int)(i / ((long)groups * Ho));
     const int ymin = bounds[2 * yo], ys = bounds[2 * yo + 1];
     const int* k = kk + (size_t)yo * ksize;
-    const uint8_t* p = tmp + ((size_t)b * Hs + ymin) * rowlen + xc;
-    int s = 1 << 21;
-    for (int y = 0; y < ys; ++y) s += p[(size_t)y * rowlen] * k[y];
-    dst[i] = (uint8_t)min(max(s >> 22, 0), 255);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(tmp) + ((size_t)b * Hs + ymin) * rowwords + gidx * 3;
+    int s[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) s[j] = 1 << 21;
+    for (int y = 0; y < ys; ++y) {
+      const int kv = __ldg(k + y);
+      const uint32_t w0 = __ldg(p + (size_t)y * rowwords), w1 = __ldg(p + (size_t)y * rowwords + 1),
+                     w2 = __ldg(p + (size_t)y * rowwords + 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[j] += (int)((w0 >> (8 * j)) & 0xFF) * kv;
+        s[4 + j] += (int)((w1 >> (8 * j)) & 0xFF) * kv;
+        s[8 + j] += (int)((w2 >> (8 * j)) & 0xFF) * kv;
+      }
+    }
+    int v[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) v[j] = min(max(s[j] >> 22, 0), 255);
+    if (dst != nullptr) {
+      uint32_t* o = reinterpret_cast<uint32_t*>(dst) + ((size_t)b * Ho + yo) * rowwords + gidx * 3;
+      o[0] = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+      o[1] = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+      o[2] = v[8] | (v[9] << 8) | (v[10] << 16) | (v[11] << 24);
+    }
+    if (dst_f16 != nullptr) {
+      const float inv = 1.f / 255.f;
+      const int x0 = gidx * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 pk = pack_px16_first(v[3 * q] * inv, v[3 * q + 1] * inv, v[3 * q + 2] * inv);
+        if (f16_layout == 0) {
+          uint4* o = reinterpret_cast<uint4*>(dst_f16 + (((size_t)b * Ho + yo) * Wo + x0 + q) * 16);
+          o[0] = pk;
+          o[1] = make_uint4(0, 0, 0, 0);
+        } else {
+          *reinterpret_cast<uint2*>(dst_f16 + (((size_t)b * (Ho + 2) + yo + 1) * (Wo + 2) + x0 + q + 1) * 4) =
+              make_uint2(pk.x, pk.y);
+        }
+      }
+    }
   }
 }
 
@@ -197,14 +246,18 @@ int pb_letterbox_u8_f16(const uint8_t* src, int B, int Hs, int Ws, void* dst, in
 
 int pb_pil_resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* tmp, uint8_t* dst, int Ho, int Wo,
                      const int32_t* bounds_h, const int32_t* kk_h, int ksize_h, const int32_t* bounds_v,
-                     const int32_t* kk_v, int ksize_v, int swap_rb, void* stream) {
-  PB_CHECK(src && tmp && dst && bounds_h && kk_h && bounds_v && kk_v, "pil_resize: null pointer");
+                     const int32_t* kk_v, int ksize_v, int swap_rb, void* dst_f16, int f16_layout, void* stream) {
+  PB_CHECK(src && tmp && (dst || dst_f16) && bounds_h && kk_h && bounds_v && kk_v, "pil_resize: null pointer");
+  PB_CHECK(Wo % 4 == 0, "pil_resize: output width %d must be a multiple of 4", Wo);
+  PB_CHECK(f16_layout == 0 || f16_layout == 1, "pil_resize: bad f16_layout");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const long t1 = (long)B * Hs * Wo;
-  pil_horizontal_kernel<<<grid_for(t1, 256), 256, 0, s>>>(src, B, Hs, Ws, tmp, Wo, bounds_h, kk_h, ksize_h, swap_rb);
+  const size_t hsmem = ((size_t)Ws * 3 + 15) & ~(size_t)15;
+  PB_CHECK(hsmem <= 48 * 1024, "pil_resize: source rows of %d pixels do not fit the row buffer", Ws);
+  pil_horizontal_kernel<<<B * Hs, 256, hsmem, s>>>(src, Ws, tmp, Wo, bounds_h, kk_h, ksize_h, swap_rb);
   PB_CUDA(cudaGetLastError());
-  const long t2 = (long)B * Ho * Wo * 3;
-  pil_vertical_kernel<<<grid_for(t2, 256), 256, 0, s>>>(tmp, B, Hs, Wo, dst, Ho, bounds_v, kk_v, ksize_v);
+  const long t2 = (long)B * Ho * (Wo / 4);
+  pil_vertical_kernel<<<grid_for(t2, 256), 256, 0, s>>>(tmp, B, Hs, Wo, dst, Ho, bounds_v, kk_v, ksize_v,
+                                                         reinterpret_cast<__half*>(dst_f16), f16_layout);
   PB_CUDA(cudaGetLastError());
   count_launch(2);
   return 0;

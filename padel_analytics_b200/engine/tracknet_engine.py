@@ -188,7 +188,8 @@ class BallPipeline:
     def _resize(self, src, n, dst, swap_rb):
         L.check(L.lib().pb_pil_resize_u8(src.data_ptr(), n, self.Hs, self.Ws, self.tmp.data_ptr(), dst.data_ptr(),
                                          self.eng.H, self.eng.W, self.bh.data_ptr(), self.kh.data_ptr(), self.ksh,
-                                         self.bv.data_ptr(), self.kv.data_ptr(), self.ksv, swap_rb, L.stream_ptr()))
+                                         self.bv.data_ptr(), self.kv.data_ptr(), self.ksv, swap_rb, None, 0,
+                                         L.stream_ptr()))
 
     def push_frames(self, frames_bgr: torch.Tensor):
         """frames: (n,Hs,Ws,3) u8 BGR, host (pinned or not) or device; n <= B+7. Resized into the ring."""

@@ -289,14 +289,13 @@ class YoloEngine:
             bv, kv, ksv = resample.pil_bicubic_tables(Hs, size)
             up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
             self._tables[key] = dict(bh=up(bh), kh=up(kh), ksh=ksh, bv=up(bv), kv=up(kv), ksv=ksv,
-                                     tmp=torch.empty((self.B, Hs, size, 3), dtype=torch.uint8, device=self.device),
-                                     dst=torch.empty((self.B, size, size, 3), dtype=torch.uint8, device=self.device))
+                                     tmp=torch.empty((self.B, Hs, size, 3), dtype=torch.uint8, device=self.device))
         t = self._tables[key]
-        L.check(L.lib().pb_pil_resize_u8(frames_dev.data_ptr(), n, Hs, Ws, t["tmp"].data_ptr(), t["dst"].data_ptr(),
+        # the vertical pass writes the normalised fp16 network input directly (no u8 round trip)
+        L.check(L.lib().pb_pil_resize_u8(frames_dev.data_ptr(), n, Hs, Ws, t["tmp"].data_ptr(), None,
                                          size, size, t["bh"].data_ptr(), t["kh"].data_ptr(), t["ksh"],
-                                         t["bv"].data_ptr(), t["kv"].data_ptr(), t["ksv"], 1, L.stream_ptr()))
-        L.check(L.lib().pb_u8_to_f16_nhwc16(t["dst"].data_ptr(), n, size, size, st["x0"].data_ptr(), 0, 1, 2, 1,
-                                            L.stream_ptr()))
+                                         t["bv"].data_ptr(), t["kv"].data_ptr(), t["ksv"], 1, st["x0"].data_ptr(), 1,
+                                         L.stream_ptr()))
         return st, (size, size)
 
     # ------------------------------------------------------------------------------------------------------

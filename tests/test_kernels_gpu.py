@@ -64,14 +64,18 @@ def test_pil_resize_bit_exact(size, hw):
     src, bh, kh, bv, kv = t(fr), t(bh), t(kh), t(bv), t(kv)
     tmp = torch.zeros((2, hw[0], Wo, 3), dtype=torch.uint8, device=DEV)
     dst = torch.zeros((2, Ho, Wo, 3), dtype=torch.uint8, device=DEV)
+    f16 = torch.zeros((2, Ho + 2, Wo + 2, 4), dtype=torch.float16, device=DEV)
     L.check(L.lib().pb_pil_resize_u8(src.data_ptr(), 2, hw[0], hw[1], tmp.data_ptr(), dst.data_ptr(), Ho, Wo,
                                      bh.data_ptr(), kh.data_ptr(), ksh, bv.data_ptr(), kv.data_ptr(), ksv, 1,
-                                     L.stream_ptr()))
+                                     f16.data_ptr(), 1, L.stream_ptr()))
     torch.cuda.synchronize()
     for i in range(2):
         ref = np.array(Image.fromarray(cv2.cvtColor(fr[i], cv2.COLOR_BGR2RGB)).resize((Wo, Ho)))
         got = dst[i].cpu().numpy()
         assert np.array_equal(got, ref), f"max diff {np.abs(got.astype(int)-ref).max()}"
+        exp16 = (torch.from_numpy(ref).float() * np.float32(1.0 / 255.0)).half()
+        assert torch.equal(f16[i, 1:-1, 1:-1, :3].cpu(), exp16)  # fused fp16 network-input output (PB_IN_STEM4)
+        assert float(f16[i, 0].abs().max()) == 0 and float(f16[i, ..., 3].abs().max()) == 0
 
 
 def test_tracknet_pack_windows():
