@@ -13,6 +13,7 @@
 // Weights are fetched per (channel block, tap group) by a second producer warp and shared by the S sub-tile MMAs.
 //
 // Replaces the same reference layers as conv_tc.cu (TrackNet Conv2DBlock models.py:5-17; ultralytics 3x3 convs).
+#include <cstdlib>
 #include <mutex>
 
 #include "conv_common.cuh"
@@ -87,7 +88,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(&tail->tmem_base, 512);
+    tmem_alloc(&tail->tmem_base, (uint32_t)kp.tmem_cols);
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < kp.cout_pad; i += blockDim.x) tail->bias[i] = kp.bias[i];
@@ -205,7 +206,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const int row = m >> 3, col = m & 7;
-    for (int tile = blockIdx.x + egroup * gridDim.x; tile < kp.total_tiles; tile += 2 * gridDim.x) {
+    for (int tile = blockIdx.x + egroup * gridDim.x; tile < kp.total_tiles; tile += kp.egroups * gridDim.x) {
       const HaloTile t = halo_decode(kp, tile);
       const int seq = (tile - blockIdx.x) / gridDim.x;
       const int acc = seq % kp.acc_stages;
@@ -261,7 +262,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, (uint32_t)kp.tmem_cols);
   }
 }
 
@@ -269,6 +270,32 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // host: geometry + tensor maps for the halo variant. Returns 0 and sets plan->variant = 1 when applicable,
 // returns -1 (no error) when the layer should use the per-tap kernel.
 // ------------------------------------------------------------------------------------------------------------
+
+// Final launch configuration shared by the halo and stem set-ups: two CTAs per SM when the tile fits in half an SM's
+// shared memory and 256 TMEM columns (light n-scale YOLO layers), else one CTA per SM with two epilogue groups.
+static void halo_finish_config(ConvPlan* plan) {
+  ConvKParams& kp = plan->kp;
+  const size_t need = (size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes + sizeof(HaloSmemTail) + 1024;
+  const char* eo = getenv("PADEL_B200_CONV_OCC2");
+  const int set_cols = kp.hs_S * kp.acc_cols;
+  const bool occ2 = (!eo || atoi(eo) != 0) && need <= 110 * 1024 && set_cols * 2 <= 256 &&
+                    kp.total_tiles > num_sms();
+  plan->smem_bytes = need;
+  if (occ2) {
+    if (kp.acc_stages * set_cols > 256) kp.acc_stages = 256 / set_cols;
+    kp.tmem_cols = 256;
+    kp.egroups = 1;
+    plan->threads = 224;
+    plan->grid = kp.total_tiles < 2 * num_sms() ? kp.total_tiles : 2 * num_sms();
+  } else {
+    if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
+    kp.tmem_cols = 512;
+    kp.egroups = 2;
+    plan->threads = kConvThreads;
+    plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+  }
+}
+
 // Stem (PB_IN_STEM4): 3x3 stride-2 conv over the padded 4-channel input. One TMA box of overlapping 16-element rows
 // (4 pixels x 4 channels, consecutive rows 2 pixels apart) holds, for a tile of 16 x 8S outputs, the three filter
 // rows r = 0..2 as [oh][r][ow] rows of 32 bytes; filter row r of sub-tile j starts at row (r*8S + 8j), 8-row groups
@@ -309,9 +336,7 @@ int conv_stem_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.tiles_h = (kp.Ho + 15) / 16;
   kp.tiles_n = kp.N;
   kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
-  plan->smem_bytes = (size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes + sizeof(HaloSmemTail) + 1024;
-  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
-  plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+  halo_finish_config(plan);
   plan->variant = 1;
   {
     // overlapping-row view of the padded (N, H+2, W+2, 4) tensor: element (k, ow, r, oh, n) =
@@ -390,7 +415,12 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.b_tx_bytes = (uint32_t)G * tap_bytes;
   kp.b_bytes = b_alloc;
   kp.a_stages = 2;
-  size_t rest = budget - (size_t)2 * kp.a_bytes;
+  // light layers: size the rings for half an SM so that two CTAs can be co-resident (see halo_finish_config)
+  const int min_b_small = G == 9 ? 2 : (G == 3 ? 3 : 4);
+  const bool small = (size_t)2 * kp.a_bytes + (size_t)min_b_small * b_alloc + sizeof(HaloSmemTail) + 1024 <= 108 * 1024 &&
+                     S * acc_cols * 2 <= 256;
+  const size_t budget2 = small ? (size_t)108 * 1024 - sizeof(HaloSmemTail) - 1024 : budget;
+  size_t rest = budget2 - (size_t)2 * kp.a_bytes;
   if (kp.kblocks > 2 && rest > (size_t)kp.a_bytes + 4 * (size_t)b_alloc) {  // a third halo buffer when K is deep
     kp.a_stages = 3;
     rest -= kp.a_bytes;
@@ -408,9 +438,7 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.tiles_h = (kp.Ho + 15) / 16;
   kp.tiles_n = kp.N;
   kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
-  plan->smem_bytes = (size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes + sizeof(HaloSmemTail) + 1024;
-  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
-  plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+  halo_finish_config(plan);
   plan->variant = 1;
 
   const CUtensorMapSwizzle swz = kp.KB == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -447,7 +475,7 @@ int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
     attr_err = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   PB_CHECK(attr_err == cudaSuccess, "conv(halo): cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
-  conv_halo_kernel<<<plan->grid, kConvThreads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->kp);
+  conv_halo_kernel<<<plan->grid, plan->threads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->kp);
   PB_CUDA(cudaGetLastError());
   count_launch();
   return 0;

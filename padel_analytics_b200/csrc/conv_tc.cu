@@ -76,7 +76,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(&tail->tmem_base, 512);
+    tmem_alloc(&tail->tmem_base, (uint32_t)kp.tmem_cols);
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < kp.cout_pad; i += blockDim.x) tail->bias[i] = kp.bias[i];
@@ -193,7 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int tw_i = p & TWm;
     const int th_i = (p >> kp.tw_log2) & THm;
     const int tn_i = p >> (kp.tw_log2 + kp.th_log2);
-    for (int tile = blockIdx.x + egroup * gridDim.x; tile < kp.total_tiles; tile += 2 * gridDim.x) {
+    for (int tile = blockIdx.x + egroup * gridDim.x; tile < kp.total_tiles; tile += kp.egroups * gridDim.x) {
       const int seq = (tile - blockIdx.x) / gridDim.x;  // per-CTA tile sequence number
       const int acc = seq % kp.acc_stages;
       const uint32_t acc_phase = (uint32_t)(seq / kp.acc_stages) & 1u;
@@ -249,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, (uint32_t)kp.tmem_cols);
   }
 }
 
@@ -414,14 +414,30 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   kp.b_tx_bytes = (uint32_t)kp.BN * kp.KB * 2u;
   kp.b_bytes = (kp.b_tx_bytes + 1023u) & ~1023u;
   const uint32_t stage_bytes = kp.a_bytes + kp.b_bytes;
-  const size_t budget = 200 * 1024;
+  // Two CTAs per SM for light layers (small stages, narrow N): each gets half the shared memory and 256 TMEM
+  // columns, so one CTA's TMA / epilogue latency is covered by the other's work.  PADEL_B200_CONV_OCC2=0 disables.
+  const char* eo = getenv("PADEL_B200_CONV_OCC2");
+  const bool occ2 = (!eo || atoi(eo) != 0) && (size_t)stage_bytes * 6 <= 96 * 1024 && kp.acc_cols * 2 <= 256 &&
+                    kp.total_tiles > num_sms();
+  const size_t budget = occ2 ? 96 * 1024 : 200 * 1024;
   int stages = (int)(budget / stage_bytes);
   if (stages > kConvMaxStages) stages = kConvMaxStages;
   PB_CHECK(stages >= 2, "conv: stage too large (%u bytes)", stage_bytes);
   kp.stages = stages;
   plan->smem_bytes = (size_t)stages * stage_bytes + sizeof(ConvSmemTail) + 1024;
-  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // force 1 CTA/SM (TMEM: 512 cols each)
-  plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+  if (occ2) {
+    if (kp.acc_stages * kp.acc_cols > 256) kp.acc_stages = 256 / kp.acc_cols;
+    kp.tmem_cols = 256;
+    kp.egroups = 1;
+    plan->threads = 224;
+    plan->grid = kp.total_tiles < 2 * num_sms() ? kp.total_tiles : 2 * num_sms();
+  } else {
+    if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // force 1 CTA/SM (TMEM: 512 cols)
+    kp.tmem_cols = 512;
+    kp.egroups = 2;
+    plan->threads = kConvThreads;
+    plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+  }
 
   const CUtensorMapSwizzle swz = kp.KB == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : kp.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -467,7 +483,7 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   PB_CHECK(attr_err == cudaSuccess, "conv: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
-  conv_tc_kernel<<<plan->grid, kConvThreads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->kp);
+  conv_tc_kernel<<<plan->grid, plan->threads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->kp);
   PB_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -57,6 +57,8 @@ struct ConvKParams {
   uint32_t idesc;
   uint32_t a_bytes, b_bytes, b_tx_bytes;
   int acc_stages, acc_cols;  // TMEM accumulator ring: acc_stages buffers, acc_cols columns apart
+  int tmem_cols;             // TMEM columns allocated by the CTA (power of two; 512 unless two CTAs share an SM)
+  int egroups;               // epilogue warp groups (2 with 352 threads, 1 with 224 threads / two CTAs per SM)
   const float* head_w;
   const float* head_b;
   int head_n;
@@ -74,6 +76,7 @@ struct ConvPlan {
   CUtensorMap tmap_a;
   CUtensorMap tmap_w;
   int grid;
+  int threads;
   size_t smem_bytes;
   int variant;  // 0 = per-tap boxes (conv_tc_kernel), 1 = shared halo tile (conv_halo_kernel)
 };
