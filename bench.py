@@ -303,26 +303,48 @@ def main():
         for k in ("players", "pose", "court"):
             for st in trackers[k].model._progs.values():
                 progs.append((k, st["prog"]))
-        conv_ms = conv_flops = conv_bytes = all_ms = 0.0
+        per_kernel = {}
         per_model = {}
+        all_ms = 0.0
         for name, p in progs:
             t = ops.time_program_ops(p, repeats=3)
+            kn = p.op_kernels()
+            for ti, k, f, by in zip(t, kn, p.flops, p.bytes):
+                e = per_kernel.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+                e["ms"] += ti
+                e["flops"] += f
+                e["bytes"] += by
+                e["launches"] += 1
             cm = sum(ti for ti, kd in zip(t, p.kinds) if kd == "conv")
             cf = sum(f for f, kd in zip(p.flops, p.kinds) if kd == "conv")
-            conv_ms += cm
-            conv_flops += cf
-            conv_bytes += sum(b for b, kd in zip(p.bytes, p.kinds) if kd == "conv")
             all_ms += sum(t)
             per_model[name] = {"conv_ms": round(cm, 3), "all_ops_ms": round(sum(t), 3),
                                "gflop_per_frame": round(cf / B / 1e9, 3), "tflops": round(cf / cm / 1e9, 1)}
         pk = _peaks()
-        achieved = conv_flops / (conv_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": round(achieved, 1),
-                "peak": pk["tflops_sustained"], "peak_kind": f"{pk['source']} cuBLAS bf16 sustained", "unit": "TFLOP/s",
-                "frac": round(achieved / pk["tflops_sustained"], 4), "traffic": None,
-                "algorithmic_gflop_per_step": round(conv_flops / 1e9, 1),
-                "algorithmic_act_gb_per_step": round(conv_bytes / 1e9, 2),
-                "conv_ms_per_step": round(conv_ms, 3), "program_ms_per_step": round(all_ms, 3), "per_model": per_model}
+        dom = max((k for k in per_kernel if k.startswith("conv")), key=lambda k: per_kernel[k]["ms"])
+        d = per_kernel[dom]
+        achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
+        conv_ms = sum(v["ms"] for k, v in per_kernel.items() if k.startswith("conv"))
+        conv_fl = sum(v["flops"] for k, v in per_kernel.items() if k.startswith("conv"))
+        traffic = None
+        tf = ROOT / "profiles" / "r01_tracknet_dram_bytes.json"
+        if tf.exists() and dom == "conv_halo_kernel":
+            traffic = json.loads(tf.read_text())
+        roof = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 1), "peak": pk["tflops_sustained"],
+                "peak_kind": f"{pk['source']} cuBLAS bf16 sustained", "unit": "TFLOP/s",
+                "frac": round(achieved / pk["tflops_sustained"], 4),
+                "traffic": (traffic or {}).get("dram_gb_per_step_tracknet_halo_launches"),
+                "traffic_note": (traffic or {}).get("note"),
+                "launches_per_step": d["launches"], "kernel_ms_per_step": round(d["ms"], 3),
+                "algorithmic_gflop_per_step": round(d["flops"] / 1e9, 1),
+                "algorithmic_act_gb_per_step": round(d["bytes"] / 1e9, 2),
+                "all_conv_kernels": {"ms_per_step": round(conv_ms, 3), "tflops": round(conv_fl / conv_ms / 1e9, 1),
+                                     "frac": round(conv_fl / conv_ms / 1e9 / pk["tflops_sustained"], 4)},
+                "program_ms_per_step": round(all_ms, 3),
+                "per_kernel": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                   "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["flops"] else 0.0,
+                                   "gbs": round(v["bytes"] / v["ms"] / 1e6, 1)} for k, v in per_kernel.items()},
+                "per_model": per_model}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

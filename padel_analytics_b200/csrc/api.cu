@@ -104,6 +104,18 @@ int pb_program_add_sppf_pool(pb_program* p, void* buf, int N, int H, int W, int 
 
 int pb_program_num_ops(const pb_program* p) { return p ? (int)p->ops.size() : 0; }
 
+int pb_program_op_kernel(const pb_program* p, int i) {
+  if (!p || i < 0 || i >= (int)p->ops.size()) return -1;
+  const Op& op = p->ops[i];
+  switch (op.kind) {
+    case OpKind::Conv: return op.conv->variant == 1 ? 1 : 0;
+    case OpKind::MaxPool2: return 2;
+    case OpKind::Upsample2: return 3;
+    case OpKind::SppfPool: return 4;
+  }
+  return -1;
+}
+
 int pb_program_run_range(pb_program* p, int first, int last, void* stream) {
   PB_CHECK(p != nullptr, "program_run: null");
   PB_CHECK(first >= 0 && last <= (int)p->ops.size() && first <= last, "program_run: bad range");

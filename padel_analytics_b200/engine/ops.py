@@ -171,6 +171,11 @@ class Program:
     def num_ops(self) -> int:
         return L.lib().pb_program_num_ops(self._h)
 
+    def op_kernels(self) -> list[str]:
+        names = {0: "conv_tc_kernel", 1: "conv_halo_kernel", 2: "maxpool2_kernel", 3: "upsample2_kernel",
+                 4: "sppf_pool_kernel"}
+        return [names[L.lib().pb_program_op_kernel(self._h, i)] for i in range(self.num_ops)]
+
     def run(self, first: int | None = None, last: int | None = None):
         if first is None:
             L.check(L.lib().pb_program_run(self._h, L.stream_ptr()))
