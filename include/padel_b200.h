@@ -123,17 +123,19 @@ int pb_letterbox_u8_f16(const uint8_t* src, int B, int Hs, int Ws, void* dst, in
  *   bounds_*: int32 [out][2] = (xmin, xsize); kk_*: int32 [out][ksize] (22-bit fixed point).
  * src u8 (B,Hs,Ws,3) -> tmp u8 (B,Hs,Wo,3) -> dst u8 (B,Ho,Wo,3) (may be NULL). swap_rb!=0 swaps channels 0/2
  * (BGR->RGB). If dst_f16 != NULL the vertical pass also writes value/255 as the fp16 network input
- * (f16_layout 0: (B,Ho,Wo,16) NHWC; 1: PB_IN_STEM4 (B,Ho+2,Wo+2,4)), saving the u8 round trip. Wo % 4 == 0.       */
+ * (f16_layout 0: (B,Ho,Wo,16) NHWC; 1: PB_IN_STEM4 (B,Ho+2,Wo+2,4); 2: plain (B,Ho,Wo,4)), saving the u8 round
+ * trip. Wo % 4 == 0.                                                                                            */
 int pb_pil_resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* tmp, uint8_t* dst, int Ho, int Wo,
                      const int32_t* bounds_h, const int32_t* kk_h, int ksize_h, const int32_t* bounds_v,
                      const int32_t* kk_v, int ksize_v, int swap_rb, void* dst_f16, int f16_layout, void* stream);
 /* u8 (B,H,W,3) -> half NHWC (B,H,W,16): dst[...,k] = src[..., ck]/255 for k<3, 0 otherwise */
 int pb_u8_to_f16_nhwc16(const uint8_t* src, int B, int H, int W, void* dst, int c0, int c1, int c2, int out_layout,
                         void* stream);
-/* TrackNet window assembly (iterable.py:167-199): frames u8 ring (T,H,W,3) RGB, median u8 (H,W,3) RGB ->
- * x half NHWC (B,H,W,32): channels [med(3), f[first+b+0](3) ... f[first+b+7](3), 0 x5], value/255.              */
-int pb_tracknet_pack_windows(const uint8_t* frames, int ring, int first_slot, const uint8_t* median, int B, int H,
-                             int W, void* x, void* stream);
+/* TrackNet window assembly (iterable.py:167-199): frames = ring of resized RGB frames as normalised fp16 4-channel
+ * pixels (ring,H,W,4) (written by pb_pil_resize_u8 with f16_layout 2), median likewise (H,W,4) ->
+ * x half NHWC (B,H,W,32): channels [med(3), f[first+b+0](3) ... f[first+b+7](3), 0 x5].                          */
+int pb_tracknet_pack_windows(const void* frames, int ring, int first_slot, const void* median, int B, int H, int W,
+                             void* x, void* stream);
 
 /* ---- YOLOv8 head decode + NMS (ultralytics Detect/Pose decode, ops.non_max_suppression) --- */
 typedef struct pb_yolo_level {

@@ -153,9 +153,11 @@ __global__ void pil_vertical_kernel(const uint8_t* __restrict__ tmp, int B, int 
           uint4* o = reinterpret_cast<uint4*>(dst_f16 + (((size_t)b * Ho + yo) * Wo + x0 + q) * 16);
           o[0] = pk;
           o[1] = make_uint4(0, 0, 0, 0);
-        } else {
+        } else if (f16_layout == 1) {
           *reinterpret_cast<uint2*>(dst_f16 + (((size_t)b * (Ho + 2) + yo + 1) * (Wo + 2) + x0 + q + 1) * 4) =
               make_uint2(pk.x, pk.y);
+        } else {  // 2: plain 4-channel pixels (B,Ho,Wo,4)
+          *reinterpret_cast<uint2*>(dst_f16 + (((size_t)b * Ho + yo) * Wo + x0 + q) * 4) = make_uint2(pk.x, pk.y);
         }
       }
     }
@@ -182,35 +184,42 @@ __global__ void u8_to_f16_nhwc16_kernel(const uint8_t* __restrict__ src, long np
   }
 }
 
-// x[b, h, w, :] = [median(3), frame[first+b+0](3), ..., frame[first+b+7](3), 0*5] / 255   (32 channels, fp16)
-__global__ void tracknet_pack_kernel(const uint8_t* __restrict__ frames, int ring, int first_slot,
-                                     const uint8_t* __restrict__ median, int B, int HW, __half* __restrict__ x) {
-  const long total = (long)B * HW * 4;  // 4 groups of 8 channels per pixel
-  const float inv = 1.f / 255.f;
+// x[b, h, w, :] = [median(3), frame[first+b+0](3), ..., frame[first+b+7](3), 0*5]   (32 channels, fp16)
+// frames / median are already normalised fp16 4-channel pixels (written by the resize pass): one thread per pixel
+// gathers nine 8-byte pixels and writes one 64-byte row.
+__global__ void tracknet_pack_kernel(const uint2* __restrict__ frames, int ring, int first_slot,
+                                     const uint2* __restrict__ median, int B, int HW, uint4* __restrict__ x) {
+  const long total = (long)B * HW;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int g = (int)(i & 3);
-    const long pixl = i >> 2;
-    const int pix = (int)(pixl % HW);
-    const int b = (int)(pixl / HW);
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = g * 8 + j;  // logical channel 0..31
-      float val = 0.f;
-      if (ch < 3) {
-        val = median[(size_t)pix * 3 + ch] * inv;
-      } else if (ch < 27) {
-        const int f = (ch - 3) / 3, c = (ch - 3) % 3;
-        const int slot = (first_slot + b + f) % ring;
-        val = frames[((size_t)slot * HW + pix) * 3 + c] * inv;
-      }
-      v[j] = val;
+    const int pix = (int)(i % HW);
+    const int b = (int)(i / HW);
+    unsigned short h[32];
+    {
+      const uint2 m = __ldg(median + pix);
+      h[0] = (unsigned short)(m.x & 0xFFFF);
+      h[1] = (unsigned short)(m.x >> 16);
+      h[2] = (unsigned short)(m.y & 0xFFFF);
     }
-    uint4 pk;
-    __half2* h = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4*>(x + (size_t)pixl * 32 + g * 8) = pk;
+    for (int f = 0; f < 8; ++f) {
+      const int slot = (first_slot + b + f) % ring;
+      const uint2 p = __ldg(frames + (size_t)slot * HW + pix);
+      h[3 + 3 * f] = (unsigned short)(p.x & 0xFFFF);
+      h[4 + 3 * f] = (unsigned short)(p.x >> 16);
+      h[5 + 3 * f] = (unsigned short)(p.y & 0xFFFF);
+    }
+#pragma unroll
+    for (int j = 27; j < 32; ++j) h[j] = 0;
+    uint4* o = x + i * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 v;
+      v.x = (uint32_t)h[8 * q + 0] | ((uint32_t)h[8 * q + 1] << 16);
+      v.y = (uint32_t)h[8 * q + 2] | ((uint32_t)h[8 * q + 3] << 16);
+      v.z = (uint32_t)h[8 * q + 4] | ((uint32_t)h[8 * q + 5] << 16);
+      v.w = (uint32_t)h[8 * q + 6] | ((uint32_t)h[8 * q + 7] << 16);
+      o[q] = v;
+    }
   }
 }
 
@@ -249,7 +258,7 @@ int pb_pil_resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* tmp, ui
                      const int32_t* kk_v, int ksize_v, int swap_rb, void* dst_f16, int f16_layout, void* stream) {
   PB_CHECK(src && tmp && (dst || dst_f16) && bounds_h && kk_h && bounds_v && kk_v, "pil_resize: null pointer");
   PB_CHECK(Wo % 4 == 0, "pil_resize: output width %d must be a multiple of 4", Wo);
-  PB_CHECK(f16_layout == 0 || f16_layout == 1, "pil_resize: bad f16_layout");
+  PB_CHECK(f16_layout >= 0 && f16_layout <= 2, "pil_resize: bad f16_layout");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t hsmem = ((size_t)Ws * 3 + 15) & ~(size_t)15;
   PB_CHECK(hsmem <= 48 * 1024, "pil_resize: source rows of %d pixels do not fit the row buffer", Ws);
@@ -275,13 +284,14 @@ int pb_u8_to_f16_nhwc16(const uint8_t* src, int B, int H, int W, void* dst, int 
   return 0;
 }
 
-int pb_tracknet_pack_windows(const uint8_t* frames, int ring, int first_slot, const uint8_t* median, int B, int H,
-                             int W, void* x, void* stream) {
+int pb_tracknet_pack_windows(const void* frames, int ring, int first_slot, const void* median, int B, int H, int W,
+                             void* x, void* stream) {
   PB_CHECK(frames && median && x, "tracknet_pack: null pointer");
   PB_CHECK(ring >= 8, "tracknet_pack: ring must hold at least 8 frames");
-  const long total = (long)B * H * W * 4;
+  const long total = (long)B * H * W;
   tracknet_pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      frames, ring, first_slot, median, B, H * W, reinterpret_cast<__half*>(x));
+      reinterpret_cast<const uint2*>(frames), ring, first_slot, reinterpret_cast<const uint2*>(median), B, H * W,
+      reinterpret_cast<uint4*>(x));
   PB_CUDA(cudaGetLastError());
   count_launch();
   return 0;

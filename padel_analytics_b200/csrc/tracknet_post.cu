@@ -67,6 +67,27 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 }
 
 // One block per frame. scratch per frame: parent, xmin, xmax, ymin, ymax (int32 [H*W] each).
+// The mask is scanned 16 bytes at a time (it is almost entirely zero); only foreground pixels touch the scratch.
+template <typename F>
+__device__ __forceinline__ void for_each_fg(const uint8_t* __restrict__ m, int HW, F f) {
+  const int nvec = HW >> 4;
+  const uint4* mv = reinterpret_cast<const uint4*>(m);
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint4 q = mv[v];
+    if ((q.x | q.y | q.z | q.w) == 0u) continue;
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (w[k] == 0u) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((w[k] >> (8 * j)) & 0xFFu) f(v * 16 + k * 4 + j);
+    }
+  }
+  for (int i = (nvec << 4) + threadIdx.x; i < HW; i += blockDim.x)
+    if (m[i]) f(i);
+}
+
 __global__ void __launch_bounds__(1024) ccl_bbox_kernel(const uint8_t* __restrict__ mask, int H, int W,
                                                         int* __restrict__ scratch, int* __restrict__ bbox) {
   const int HW = H * W;
@@ -85,16 +106,14 @@ __global__ void __launch_bounds__(1024) ccl_bbox_kernel(const uint8_t* __restric
   }
   __syncthreads();
   int mine = 0;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    if (m[i]) {
-      parent[i] = i;
-      xmin[i] = W;
-      xmax[i] = -1;
-      ymin[i] = H;
-      ymax[i] = -1;
-      mine = 1;
-    }
-  }
+  for_each_fg(m, HW, [&](int i) {
+    parent[i] = i;
+    xmin[i] = W;
+    xmax[i] = -1;
+    ymin[i] = H;
+    ymax[i] = -1;
+    mine = 1;
+  });
   if (mine) any = 1;
   __threadfence_block();
   __syncthreads();
@@ -102,8 +121,7 @@ __global__ void __launch_bounds__(1024) ccl_bbox_kernel(const uint8_t* __restric
     if (threadIdx.x < 4) bbox[f * 4 + threadIdx.x] = 0;
     return;
   }
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    if (!m[i]) continue;
+  for_each_fg(m, HW, [&](int i) {
     const int x = i % W, y = i / W;
     if (x > 0 && m[i - 1]) uf_union(parent, i, i - 1);
     if (y > 0) {
@@ -111,26 +129,25 @@ __global__ void __launch_bounds__(1024) ccl_bbox_kernel(const uint8_t* __restric
       if (x > 0 && m[i - W - 1]) uf_union(parent, i, i - W - 1);
       if (x < W - 1 && m[i - W + 1]) uf_union(parent, i, i - W + 1);
     }
-  }
+  });
   __threadfence_block();
   __syncthreads();
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    if (!m[i]) continue;
+  for_each_fg(m, HW, [&](int i) {
     const int r = uf_find(parent, i);
     const int x = i % W, y = i / W;
     atomicMin(xmin + r, x);
     atomicMax(xmax + r, x);
     atomicMin(ymin + r, y);
     atomicMax(ymax + r, y);
-  }
+  });
   __threadfence_block();
   __syncthreads();
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    if (!m[i] || __ldcg(parent + i) != i) continue;
+  for_each_fg(m, HW, [&](int i) {
+    if (__ldcg(parent + i) != i) return;
     const int w = __ldcg(xmax + i) - __ldcg(xmin + i) + 1, h = __ldcg(ymax + i) - __ldcg(ymin + i) + 1;
     const unsigned long long key = ((unsigned long long)(unsigned)(w * h) << 32) | (unsigned)i;
     atomicMax(&best, key);  // max area; ties -> largest root index (latest first pixel in raster order)
-  }
+  });
   __syncthreads();
   if (threadIdx.x == 0) {
     const int r = (int)(best & 0xffffffffull);
@@ -171,6 +188,7 @@ int pb_tracknet_ensemble(const float* pred, int S, int first_window, int total_w
 
 int pb_ccl_bbox(const uint8_t* mask, int nframes, int H, int W, int* scratch, int* bbox, void* stream) {
   PB_CHECK(mask && scratch && bbox, "ccl: null pointer");
+  PB_CHECK((H * W) % 16 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0, "ccl: H*W must be a multiple of 16");
   if (nframes <= 0) return 0;
   ccl_bbox_kernel<<<nframes, 1024, 0, static_cast<cudaStream_t>(stream)>>>(mask, H, W, scratch, bbox);
   PB_CUDA(cudaGetLastError());

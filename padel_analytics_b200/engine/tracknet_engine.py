@@ -159,10 +159,10 @@ class BallPipeline:
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
         self.bh, self.kh, self.bv, self.kv = up(bh), up(kh), up(bv), up(kv)
         self.ring = B + 8
-        self.small = torch.zeros((self.ring, H, W, 3), dtype=torch.uint8, device=self.dev)  # resized RGB frames
+        # resized RGB frames as normalised fp16 4-channel pixels (what the window-packing kernel gathers from)
+        self.small = torch.zeros((self.ring, H, W, 4), dtype=torch.float16, device=self.dev)
         self.tmp = torch.zeros((B + 7, self.Hs, W, 3), dtype=torch.uint8, device=self.dev)
         self.stage = torch.zeros((B + 7, self.Hs, self.Ws, 3), dtype=torch.uint8, device=self.dev)
-        self.small_stage = torch.zeros((B + 7, H, W, 3), dtype=torch.uint8, device=self.dev)
         self.mask = torch.zeros((B + 7, H, W), dtype=torch.uint8, device=self.dev)
         self.scratch = torch.zeros((B + 7, 5, H * W), dtype=torch.int32, device=self.dev)
         self.bbox = torch.zeros((B + 7, 4), dtype=torch.int32, device=self.dev)
@@ -173,7 +173,7 @@ class BallPipeline:
         if med.shape[:2] != (self.Hs, self.Ws):
             raise L.PbError("median must have the frame resolution")
         med = med.to(torch.uint8).to(self.dev).contiguous().view(1, self.Hs, self.Ws, 3)
-        self.median_small = torch.zeros((1, H, W, 3), dtype=torch.uint8, device=self.dev)
+        self.median_small = torch.zeros((1, H, W, 4), dtype=torch.float16, device=self.dev)
         self._resize(med, 1, self.median_small, swap_rb=0)
         self.reset()
 
@@ -185,11 +185,12 @@ class BallPipeline:
         self.n_windows = 0  # windows processed
         self.eng.pred.zero_()
 
-    def _resize(self, src, n, dst, swap_rb):
-        L.check(L.lib().pb_pil_resize_u8(src.data_ptr(), n, self.Hs, self.Ws, self.tmp.data_ptr(), dst.data_ptr(),
+    def _resize(self, src, n, dst_f16, swap_rb):
+        """Pillow-exact resize of n frames; the vertical pass writes value/255 as fp16 4-channel pixels into dst_f16."""
+        L.check(L.lib().pb_pil_resize_u8(src.data_ptr(), n, self.Hs, self.Ws, self.tmp.data_ptr(), None,
                                          self.eng.H, self.eng.W, self.bh.data_ptr(), self.kh.data_ptr(), self.ksh,
-                                         self.bv.data_ptr(), self.kv.data_ptr(), self.ksv, swap_rb, None, 0,
-                                         L.stream_ptr()))
+                                         self.bv.data_ptr(), self.kv.data_ptr(), self.ksv, swap_rb, dst_f16.data_ptr(),
+                                         2, L.stream_ptr()))
 
     def push_frames(self, frames_bgr: torch.Tensor):
         """frames: (n,Hs,Ws,3) u8 BGR, host (pinned or not) or device; n <= B+7. Resized into the ring."""
@@ -199,14 +200,14 @@ class BallPipeline:
         if frames_bgr.device.type != "cuda":
             self.stage[:n].copy_(frames_bgr, non_blocking=True)
             frames_bgr = self.stage[:n]
-        self._resize(frames_bgr.contiguous(), n, self.small_stage, swap_rb=1)
         if self.n_frames_in + n > self.n_windows + self.ring:
             raise L.PbError("BallPipeline: frame ring overflow (process windows before pushing more frames)")
+        frames_bgr = frames_bgr.contiguous()
         start = self.n_frames_in % self.ring
-        first = min(n, self.ring - start)
-        self.small[start:start + first].copy_(self.small_stage[:first])
+        first = min(n, self.ring - start)  # resize straight into the ring (two runs when it wraps)
+        self._resize(frames_bgr[:first], first, self.small[start:start + first], swap_rb=1)
         if first < n:
-            self.small[: n - first].copy_(self.small_stage[first:n])
+            self._resize(frames_bgr[first:], n - first, self.small[: n - first], swap_rb=1)
         self.n_frames_in += n
 
     def windows_ready(self) -> int:

@@ -83,9 +83,11 @@ def test_tracknet_pack_windows():
     ring, B, H, W = 12, 4, 32, 64
     frames = rng.integers(0, 256, (ring, H, W, 3), dtype=np.uint8)
     med = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    to4 = lambda a: torch.cat([(torch.from_numpy(a).float() * np.float32(1 / 255.0)).half(),
+                               torch.zeros(a.shape[:-1] + (1,), dtype=torch.float16)], -1).contiguous().to(DEV)
     x = torch.zeros((B, H, W, 32), dtype=torch.float16, device=DEV)
     first = 7
-    fd, md = torch.from_numpy(frames).to(DEV), torch.from_numpy(med).to(DEV)
+    fd, md = to4(frames), to4(med)
     L.check(L.lib().pb_tracknet_pack_windows(fd.data_ptr(), ring, first, md.data_ptr(), B, H, W, x.data_ptr(),
                                              L.stream_ptr()))
     torch.cuda.synchronize()
