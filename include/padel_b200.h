@@ -99,9 +99,13 @@ int pb_program_add_upsample2(pb_program* p, const void* in, int N, int H, int W,
                              void* out, int out_C, int out_coff);
 /* SPPF pooling: slice0=[0,c) of buf is x'; writes maxpool5, maxpool5^2, maxpool5^3 into slices 1..3 */
 int pb_program_add_sppf_pool(pb_program* p, void* buf, int N, int H, int W, int C, int c);
+/* 1x1 conv (C -> n_out <= 8) + bias + sigmoid, half NHWC (N,H,W,C) -> float NCHW (N,n_out,H,W): the TrackNet predictor
+ * (models.py:55,72-73). weight float [n_out][C], bias float [n_out]. */
+int pb_program_add_pointwise_head(pb_program* p, const void* in, int N, int H, int W, int C, const float* weight,
+                                  const float* bias, int n_out, float* out);
 int pb_program_num_ops(const pb_program* p);
 /* Kernel that op i launches: 0 conv_tc_kernel (per-tap boxes), 1 conv_halo_kernel (shared halo / stem), 2 maxpool2,
- * 3 upsample2, 4 sppf_pool; -1 if i is out of range. */
+ * 3 upsample2, 4 sppf_pool, 5 pointwise_head; -1 if i is out of range. */
 int pb_program_op_kernel(const pb_program* p, int i);
 int pb_program_run(pb_program* p, void* stream);
 /* Run ops [first, last) only (per-layer timing / debugging). */

@@ -52,6 +52,7 @@ SIGNATURES = {
     "pb_program_add_maxpool2": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i]),
     "pb_program_add_upsample2": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i]),
     "pb_program_add_sppf_pool": (_i, [_p, _p, _i, _i, _i, _i, _i]),
+    "pb_program_add_pointwise_head": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p]),
     "pb_program_num_ops": (_i, [_p]),
     "pb_program_op_kernel": (_i, [_p, _i]),
     "pb_program_run": (_i, [_p, _p]),

@@ -31,7 +31,7 @@ int num_sms() {
   return sms;
 }
 
-enum class OpKind { Conv, MaxPool2, Upsample2, SppfPool };
+enum class OpKind { Conv, MaxPool2, Upsample2, SppfPool, PointwiseHead };
 
 struct Op {
   OpKind kind;
@@ -40,6 +40,8 @@ struct Op {
   const void* in = nullptr;
   void* out = nullptr;
   int N = 0, H = 0, W = 0, C = 0, c_off = 0, c = 0, out_C = 0, out_coff = 0;
+  const float* hw = nullptr;  // pointwise head weights / bias
+  const float* hb = nullptr;
 };
 
 }  // namespace pb
@@ -102,6 +104,14 @@ int pb_program_add_sppf_pool(pb_program* p, void* buf, int N, int H, int W, int 
   return add_simple(p, OpKind::SppfPool, buf, N, H, W, C, 0, c, buf, C, 0);
 }
 
+int pb_program_add_pointwise_head(pb_program* p, const void* in, int N, int H, int W, int C, const float* weight,
+                                  const float* bias, int n_out, float* out) {
+  if (add_simple(p, OpKind::PointwiseHead, in, N, H, W, C, 0, n_out, out, 0, 0)) return 1;
+  p->ops.back().hw = weight;
+  p->ops.back().hb = bias;
+  return 0;
+}
+
 int pb_program_num_ops(const pb_program* p) { return p ? (int)p->ops.size() : 0; }
 
 int pb_program_op_kernel(const pb_program* p, int i) {
@@ -112,6 +122,7 @@ int pb_program_op_kernel(const pb_program* p, int i) {
     case OpKind::MaxPool2: return 2;
     case OpKind::Upsample2: return 3;
     case OpKind::SppfPool: return 4;
+    case OpKind::PointwiseHead: return 5;
   }
   return -1;
 }
@@ -132,6 +143,9 @@ int pb_program_run_range(pb_program* p, int first, int last, void* stream) {
         rc = launch_upsample2(op.in, op.N, op.H, op.W, op.C, op.c_off, op.c, op.out, op.out_C, op.out_coff, s);
         break;
       case OpKind::SppfPool: rc = launch_sppf_pool(op.out, op.N, op.H, op.W, op.C, op.c, s); break;
+      case OpKind::PointwiseHead:
+        rc = launch_pointwise_head(op.in, op.N, op.H, op.W, op.C, op.hw, op.hb, op.c, static_cast<float*>(op.out), s);
+        break;
     }
     if (rc) return rc;
   }

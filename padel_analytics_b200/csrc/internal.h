@@ -97,5 +97,7 @@ int launch_maxpool2(const void* in, int N, int H, int W, int C, int c_off, int c
 int launch_upsample2(const void* in, int N, int H, int W, int C, int c_off, int c, void* out, int out_C,
                      int out_coff, cudaStream_t s);
 int launch_sppf_pool(void* buf, int N, int H, int W, int C, int c, cudaStream_t s);
+int launch_pointwise_head(const void* in, int N, int H, int W, int C, const float* w, const float* b, int n_out,
+                          float* out, cudaStream_t s);
 
 }  // namespace pb

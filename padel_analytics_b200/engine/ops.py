@@ -161,6 +161,15 @@ class Program:
         L.check(L.lib().pb_program_add_sppf_pool(self._h, buf.data_ptr(), N, H, W, Ct, c))
         self._note("sppf", N * H * W * c * 2 * 4.0)
 
+    def pointwise_head(self, x, weight, bias, out):
+        N, H, W, Ct = x.shape
+        L.check(L.lib().pb_program_add_pointwise_head(self._h, x.data_ptr(), N, H, W, Ct, weight.data_ptr(),
+                                                      bias.data_ptr(), weight.shape[0], out.data_ptr()))
+        self.kinds.append("head")
+        self.descs.append(None)
+        self.flops.append(2.0 * N * H * W * Ct * weight.shape[0])
+        self.bytes.append(float(N * H * W * (Ct * 2 + weight.shape[0] * 4)))
+
     def _note(self, kind: str, nbytes: float):
         self.kinds.append(kind)
         self.descs.append(None)
@@ -173,7 +182,7 @@ class Program:
 
     def op_kernels(self) -> list[str]:
         names = {0: "conv_tc_kernel", 1: "conv_halo_kernel", 2: "maxpool2_kernel", 3: "upsample2_kernel",
-                 4: "sppf_pool_kernel"}
+                 4: "sppf_pool_kernel", 5: "pointwise_head_kernel"}
         return [names[L.lib().pb_program_op_kernel(self._h, i)] for i in range(self.num_ops)]
 
     def run(self, first: int | None = None, last: int | None = None):

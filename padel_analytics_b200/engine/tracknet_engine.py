@@ -61,7 +61,8 @@ class TrackNetEngine:
                                    sd[f"{p}.bn.bias"].float(), sd[f"{p}.bn.running_mean"].float(),
                                    sd[f"{p}.bn.running_var"].float(), 1e-5)
                 self._w[p] = ops.pack_conv_weight(w, b, ops.pad16(ci) if ci != 27 else 32, cout, self.device)
-        # predictor 1x1 (64 -> 8) + sigmoid is fused into up_block_3.conv_2's epilogue (fp32, straight from TMEM)
+        # predictor 1x1 (64 -> 8) + sigmoid: a dedicated HBM-bound kernel (the fused-epilogue variant of the conv
+        # kernel exists but costs more: 512 FMAs per pixel on 8 epilogue warps stall the MMA pipeline)
         self._head_w = sd["predictor.weight"].float().reshape(8, 64).contiguous().to(self.device)
         self._head_b = sd["predictor.bias"].float().contiguous().to(self.device)
         self._build()
@@ -84,7 +85,7 @@ class TrackNetEngine:
         self.ba, self.bb = h(H // 8, W // 8, 512), h(H // 8, W // 8, 512)
         self.u1a, self.u1b = h(H // 4, W // 4, 256), h(H // 4, W // 4, 256)
         self.u2a = h(H // 2, W // 2, 128)
-        self.u3a = h(H, W, 64)
+        self.u3a, self.u3b = h(H, W, 64), h(H, W, 64)
         # 7 carried windows + B new ones (ball_tracker.py:427-436, :523)
         self.pred = torch.zeros((7 + B, 8, H, W), dtype=torch.float32, device=dev)
 
@@ -118,10 +119,8 @@ class TrackNetEngine:
         conv(self.u2a, 0, 128, "up_block_2.conv_2", self.cat3, 0, UP)
         conv(self.cat3, 0, 192, "up_block_3.conv_1", self.u3a, 0)
         self._pred_new = self.pred[7:]
-        w, b = W_["up_block_3.conv_2"]
-        P.conv(ops.make_conv_desc(self.u3a, 0, 64, w, b, 3, 1, R, None, 0, L.OUT_NONE,
-                                  head=(self._head_w, self._head_b, self._pred_new)))
-        P.flops[-1] += 2.0 * self.B * self.H * self.W * 64 * 8  # the fused predictor's MACs
+        conv(self.u3a, 0, 64, "up_block_3.conv_2", self.u3b, 0)
+        P.pointwise_head(self.u3b, self._head_w, self._head_b, self._pred_new)
         self.prog = P
 
     # -- execution ---------------------------------------------------------------------------------------------

@@ -65,6 +65,13 @@ class Result:
     orig_shape: tuple
 
 
+def _kpad(c: int) -> int:
+    """Channel count a conv should READ: widths in (32, 64) or not a multiple of 64 above that are rounded up to a
+    multiple of 64 (zero channels in the buffer, zero weights), so the kernel runs 64-channel K blocks (128-byte rows,
+    one TMA box per tap) instead of three to five 16/32-channel blocks."""
+    return c if (c <= 32 or c % 64 == 0) else (c + 63) // 64 * 64
+
+
 def _fold(sd, p, eps=1e-3):
     return ops.fold_bn(sd[f"{p}.conv.weight"].float(), sd[f"{p}.bn.weight"].float(), sd[f"{p}.bn.bias"].float(),
                        sd[f"{p}.bn.running_mean"].float(), sd[f"{p}.bn.running_var"].float(), eps)
@@ -145,14 +152,15 @@ class YoloEngine:
             while f"{pre}.m.{n}.cv1.conv.weight" in sd:
                 n += 1
             _, h, w_, _ = x.shape
-            cat = buf(h, w_, (2 + n) * c)
+            ccat = _kpad((2 + n) * c)
+            cat = buf(h, w_, ccat)
             tmp = buf(h, w_, c)
             conv(x, coff, cin, f"{pre}.cv1", cat, 0, 1, 1)
             for j in range(n):
                 conv(cat, (1 + j) * c, c, f"{pre}.m.{j}.cv1", tmp, 0, 3, 1)
                 conv(tmp, 0, c, f"{pre}.m.{j}.cv2", cat, (2 + j) * c, 3, 1, res=cat if shortcut else None,
                      res_off=(1 + j) * c)
-            conv(cat, 0, (2 + n) * c, f"{pre}.cv2", out, ooff, 1, 1)
+            conv(cat, 0, ccat, f"{pre}.cv2", out, ooff, 1, 1)
 
         c0, c1, c2, c3, c4 = (self._cout(f"model.{i}") for i in (0, 1, 3, 5, 7))
         for c in (c0, c1, c2, c3, c4):
@@ -213,7 +221,7 @@ class YoloEngine:
             feat = buf(h, w_, fC, torch.float32)
             for name, cout_real, off in branches:
                 pre = f"model.22.{name}.{l}"
-                cm = ops.pad16(self._cout(f"{pre}.0"))
+                cm = _kpad(ops.pad16(self._cout(f"{pre}.0")))
                 t1, t2 = buf(h, w_, cm), buf(h, w_, cm)
                 conv(f, 0, cf, f"{pre}.0", t1, 0, 3, 1)
                 conv(t1, 0, cm, f"{pre}.1", t2, 0, 3, 1)
