@@ -348,11 +348,11 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   plan->variant = 0;
   if (stem) return conv_stem_setup(d, plan, encode);
   {
-    // halo variant for 3x3/s1 layers: default on for cout <= 128 (the layers the per-tap kernel leaves
+    // halo variant for 3x3/s1 layers: default on for cout <= 192 (the layers the per-tap kernel leaves
     // L2/TMA-bound); PADEL_B200_CONV_HALO=0 disables it, =1 forces it wherever it applies
     const char* e = getenv("PADEL_B200_CONV_HALO");
     const int mode = e ? atoi(e) : 2;
-    if (mode == 1 || (mode == 2 && d->cout_pad <= 128)) {
+    if (mode == 1 || (mode == 2 && d->cout_pad <= 192)) {
       const int rc = conv_halo_setup(d, plan, encode);
       if (rc >= 0) return rc;
     }

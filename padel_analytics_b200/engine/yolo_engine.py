@@ -219,12 +219,24 @@ class YoloEngine:
         for l, (f, cf, st) in enumerate(((o3, c2, 8), (o4, c3, 16), (o5, c4, 32))):
             _, h, w_, _ = f.shape
             feat = buf(h, w_, fC, torch.float32)
-            for name, cout_real, off in branches:
+            # the branches' first 3x3 convs all read `f`: run them as ONE conv (weights concatenated along cout) so the
+            # level's feature map is fetched once; each branch then reads its channel slice of the merged tensor
+            widths = [_kpad(ops.pad16(self._cout(f"model.22.{name}.{l}.0"))) for name, _, _ in branches]
+            key = ("head0", l)
+            if key not in self._packed:
+                ws, bs = zip(*(ops.pack_conv_weight(*_fold(sd, f"model.22.{name}.{l}.0"), cf, wd, dev)
+                               for (name, _, _), wd in zip(branches, widths)))
+                self._packed[key] = (torch.cat(ws, 1).contiguous(), torch.cat(bs, 0).contiguous())
+            wm, bm = self._packed[key]
+            t1m = buf(h, w_, sum(widths))
+            P.conv(ops.make_conv_desc(f, 0, cf, wm, bm, 3, 1, SILU, t1m, 0),
+                   cin_real=sd[f"model.22.cv2.{l}.0.conv.weight"].shape[1],
+                   cout_real=sum(self._cout(f"model.22.{name}.{l}.0") for name, _, _ in branches))
+            for bi, (name, cout_real, off) in enumerate(branches):
                 pre = f"model.22.{name}.{l}"
-                cm = _kpad(ops.pad16(self._cout(f"{pre}.0")))
-                t1, t2 = buf(h, w_, cm), buf(h, w_, cm)
-                conv(f, 0, cf, f"{pre}.0", t1, 0, 3, 1)
-                conv(t1, 0, cm, f"{pre}.1", t2, 0, 3, 1)
+                cm = widths[bi]
+                t2 = buf(h, w_, cm)
+                conv(t1m, sum(widths[:bi]), cm, f"{pre}.1", t2, 0, 3, 1)
                 w, b = self._wb(f"{pre}.2", cm, ops.pad16(cout_real), bn=False)
                 P.conv(ops.make_conv_desc(t2, 0, cm, w, b, 1, 1, L.ACT_NONE, feat, off, L.OUT_F32_NHWC, cout_real),
                        cin_real=self.sd[f"{pre}.2.weight"].shape[1], cout_real=cout_real)
