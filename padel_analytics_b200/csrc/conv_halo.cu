@@ -40,11 +40,12 @@ struct HaloSmemTail {
 struct HaloTile {
   int tw, th, n;
 };
-__device__ __forceinline__ HaloTile halo_decode(const ConvKParams& kp, int tile) {
+// pair mode: a "tile" is two vertically adjacent 16-row tiles, one per CTA of the pair (crank = 0 / 1)
+__device__ __forceinline__ HaloTile halo_decode(const ConvKParams& kp, int tile, uint32_t crank) {
   HaloTile t;
   t.tw = tile % kp.tiles_w;
   const int q = tile / kp.tiles_w;
-  t.th = q % kp.tiles_h;
+  t.th = kp.pair ? (q % kp.tiles_h) * 2 + (int)crank : q % kp.tiles_h;
   t.n = q / kp.tiles_h;
   return t;
 }
@@ -69,6 +70,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int S = kp.hs_S, G = kp.hs_G;
   const uint32_t row_bytes = (uint32_t)kp.KB * 2u;
   const int tap_groups = kp.hs_ntaps / G;
+  // CTA-pair mode (cluster of 2, cta_group::2): both CTAs load their own halo and half of the weights, the even
+  // CTA issues M=256 UMMAs over both, so every SM reads only half of B from its shared memory.
+  const int pair = kp.pair;
+  const uint32_t crank = pair ? cluster_ctarank() : 0u;
+  const int cta0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int cstride = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_a);
   if (warp == 6 && lane == 0) tma_prefetch_desc(&tmap_w);
@@ -83,17 +90,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < kp.acc_stages; ++i) {
       mbar_init(&tail->tmem_full[i], 1);
-      mbar_init(&tail->tmem_empty[i], 4);
+      mbar_init(&tail->tmem_empty[i], pair ? 8 : 4);  // one arrive per epilogue warp (of both CTAs in pair mode)
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(&tail->tmem_base, (uint32_t)kp.tmem_cols);
-    tmem_relinquish();
+    if (pair) {
+      tmem_alloc2(&tail->tmem_base, (uint32_t)kp.tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(&tail->tmem_base, (uint32_t)kp.tmem_cols);
+      tmem_relinquish();
+    }
   }
   for (int i = threadIdx.x; i < kp.cout_pad; i += blockDim.x) tail->bias[i] = kp.bias[i];
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
@@ -102,17 +115,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
-        const HaloTile t = halo_decode(kp, tile);
-        const int seq = (tile - blockIdx.x) / gridDim.x;
+      for (int tile = cta0; tile < kp.total_tiles; tile += cstride) {
+        const HaloTile t = halo_decode(kp, tile, crank);
+        const int seq = (tile - cta0) / cstride;
         const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
         if (dbg) kp.dbg[(0 * 64 + seq) * 4 + 0] = clock64();
         for (int cb = 0; cb < kp.kblocks; ++cb) {
           mbar_wait(&tail->a_empty[st], ph ^ 1);
           if (dbg && cb == 0) kp.dbg[(0 * 64 + seq) * 4 + 1] = clock64();
-          mbar_arrive_expect_tx(&tail->a_full[st], kp.halo_bytes);
-          tma_load_5d(a_base + (size_t)st * kp.a_bytes, &tmap_a, &tail->a_full[st], kp.c_in_off + cb * kp.KB,
-                      t.tw * 8 * S + kp.hs_x0, 0, t.th * 16 + kp.hs_y0, t.n);
+          if (pair) {
+            if (crank == 0) mbar_arrive_expect_tx(&tail->a_full[st], 2u * kp.halo_bytes);  // both CTAs' halos
+            tma_load_5d_2sm(a_base + (size_t)st * kp.a_bytes, &tmap_a, &tail->a_full[st], kp.c_in_off + cb * kp.KB,
+                            t.tw * 8 * S + kp.hs_x0, 0, t.th * 16 + kp.hs_y0, t.n);
+          } else {
+            mbar_arrive_expect_tx(&tail->a_full[st], kp.halo_bytes);
+            tma_load_5d(a_base + (size_t)st * kp.a_bytes, &tmap_a, &tail->a_full[st], kp.c_in_off + cb * kp.KB,
+                        t.tw * 8 * S + kp.hs_x0, 0, t.th * 16 + kp.hs_y0, t.n);
+          }
           if (++st == kp.a_stages) {
             st = 0;
             ph ^= 1;
@@ -126,12 +145,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
+      for (int tile = cta0; tile < kp.total_tiles; tile += cstride) {
         for (int cb = 0; cb < kp.kblocks; ++cb) {
           for (int tg = 0; tg < tap_groups; ++tg) {
             mbar_wait(&tail->b_empty[st], ph ^ 1);
-            mbar_arrive_expect_tx(&tail->b_full[st], kp.b_tx_bytes);
-            tma_load_3d(b_base + (size_t)st * kp.b_bytes, &tmap_w, &tail->b_full[st], cb * kp.KB, 0, tg * G);
+            if (pair) {  // each CTA fetches its half of the output channels
+              if (crank == 0) mbar_arrive_expect_tx(&tail->b_full[st], 2u * kp.b_tx_bytes);
+              tma_load_3d_2sm(b_base + (size_t)st * kp.b_bytes, &tmap_w, &tail->b_full[st], cb * kp.KB,
+                              (int)crank * (kp.BN / 2), tg * G);
+            } else {
+              mbar_arrive_expect_tx(&tail->b_full[st], kp.b_tx_bytes);
+              tma_load_3d(b_base + (size_t)st * kp.b_bytes, &tmap_w, &tail->b_full[st], cb * kp.KB, 0, tg * G);
+            }
             if (++st == kp.b_stages) {
               st = 0;
               ph ^= 1;
@@ -142,15 +167,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== UMMA issuer =====================
-    if (lane == 0) {
+    // ===================== UMMA issuer (pair mode: the even CTA only) =====================
+    if (lane == 0 && crank == 0) {
       int ast = 0, bst = 0, acc = 0;
       uint32_t aph = 0, bph = 0, acc_ph = 0;
       const int ksteps = kp.KB / 16;
       const uint32_t sbo = (uint32_t)kp.hs_sbo_rows * row_bytes;
-      const uint32_t tap_b_bytes = (uint32_t)kp.BN * row_bytes;
-      for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
-        const int seq = (tile - blockIdx.x) / gridDim.x;
+      const uint32_t tap_b_bytes = (uint32_t)(pair ? kp.BN / 2 : kp.BN) * row_bytes;
+      for (int tile = cta0; tile < kp.total_tiles; tile += cstride) {
+        const int seq = (tile - cta0) / cstride;
         const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
         if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 0] = clock64();
         mbar_wait(&tail->tmem_empty[acc], acc_ph ^ 1);
@@ -174,24 +199,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint64_t adesc = umma_desc_sbo(halo + (toff + 8u * (uint32_t)j) * row_bytes, row_bytes, sbo);
                 const uint32_t dj = d0 + (uint32_t)(j * kp.acc_cols);
 #pragma unroll 4
-                for (int k = 0; k < ksteps; ++k)
-                  umma_f16(dj, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kp.idesc,
-                           (uint32_t)((cb | tap | k) != 0));
+                for (int k = 0; k < ksteps; ++k) {
+                  if (pair)
+                    umma_f16_2sm(dj, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kp.idesc,
+                                 (uint32_t)((cb | tap | k) != 0));
+                  else
+                    umma_f16(dj, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kp.idesc,
+                             (uint32_t)((cb | tap | k) != 0));
+                }
               }
             }
-            umma_commit(&tail->b_empty[bst]);
+            if (pair) umma_commit_2sm(&tail->b_empty[bst]); else umma_commit(&tail->b_empty[bst]);
             if (++bst == kp.b_stages) {
               bst = 0;
               bph ^= 1;
             }
           }
-          umma_commit(&tail->a_empty[ast]);
+          if (pair) umma_commit_2sm(&tail->a_empty[ast]); else umma_commit(&tail->a_empty[ast]);
           if (++ast == kp.a_stages) {
             ast = 0;
             aph ^= 1;
           }
         }
-        umma_commit(&tail->tmem_full[acc]);
+        if (pair) umma_commit_2sm(&tail->tmem_full[acc]); else umma_commit(&tail->tmem_full[acc]);
         if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 3] = clock64();
         if (++acc == kp.acc_stages) {
           acc = 0;
@@ -206,9 +236,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const int row = m >> 3, col = m & 7;
-    for (int tile = blockIdx.x + egroup * gridDim.x; tile < kp.total_tiles; tile += kp.egroups * gridDim.x) {
-      const HaloTile t = halo_decode(kp, tile);
-      const int seq = (tile - blockIdx.x) / gridDim.x;
+    for (int tile = cta0 + egroup * cstride; tile < kp.total_tiles; tile += kp.egroups * cstride) {
+      const HaloTile t = halo_decode(kp, tile, crank);
+      const int seq = (tile - cta0) / cstride;
       const int acc = seq % kp.acc_stages;
       const uint32_t acc_ph = (uint32_t)(seq / kp.acc_stages) & 1u;
       const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64 && (threadIdx.x == 64 || threadIdx.x == 224);
@@ -253,16 +283,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+      if (lane == 0) {
+        if (pair) mbar_arrive_cluster(&tail->tmem_empty[acc], 0);  // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(&tail->tmem_empty[acc]);
+      }
       if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 2] = clock64();
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)kp.tmem_cols);
+    if (pair) tmem_dealloc2(tmem_base, (uint32_t)kp.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)kp.tmem_cols);
   }
 }
 
@@ -278,7 +313,7 @@ static void halo_finish_config(ConvPlan* plan) {
   const size_t need = (size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes + sizeof(HaloSmemTail) + 1024;
   const char* eo = getenv("PADEL_B200_CONV_OCC2");
   const int set_cols = kp.hs_S * kp.acc_cols;
-  const bool occ2 = (!eo || atoi(eo) != 0) && need <= 110 * 1024 && set_cols * 2 <= 256 &&
+  const bool occ2 = !kp.pair && (!eo || atoi(eo) != 0) && need <= 110 * 1024 && set_cols * 2 <= 256 &&
                     kp.total_tiles > num_sms();
   plan->smem_bytes = need;
   if (occ2) {
@@ -293,6 +328,10 @@ static void halo_finish_config(ConvPlan* plan) {
     kp.egroups = 2;
     plan->threads = kConvThreads;
     plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+    if (kp.pair) {  // total_tiles counts pair tiles: two CTAs each
+      const int pairs = kp.total_tiles < num_sms() / 2 ? kp.total_tiles : num_sms() / 2;
+      plan->grid = 2 * pairs;
+    }
   }
 }
 
@@ -399,6 +438,13 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   const uint32_t b_alloc = ((uint32_t)G * tap_bytes + 1023u) & ~1023u;
   if (bestS == 0) return -1;
   const int S = bestS, P = 8 * S + 2;
+  // CTA-pair mode (cta_group::2): halves the weight bytes each SM reads per UMMA -- pays off on the operand-bound
+  // N = 64/128 layers with enough rows to pair up.  PADEL_B200_CONV_PAIR=0/1 overrides.
+  {
+    const char* ep = getenv("PADEL_B200_CONV_PAIR");
+    const int pm = ep ? atoi(ep) : 0;
+    kp.pair = (pm == 1 && BN % 32 == 0 && BN >= 32 && kp.Ho >= 32) ? 1 : 0;
+  }
   kp.hs_S = S;
   kp.hs_P = P;
   kp.hs_G = G;
@@ -412,7 +458,7 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.n_ntiles = 1;
   kp.halo_bytes = 18u * (uint32_t)P * row_bytes;
   kp.a_bytes = (kp.halo_bytes + 1023u) & ~1023u;
-  kp.b_tx_bytes = (uint32_t)G * tap_bytes;
+  kp.b_tx_bytes = (uint32_t)G * tap_bytes / (kp.pair ? 2u : 1u);  // per CTA
   kp.b_bytes = b_alloc;
   kp.a_stages = 2;
   // light layers: size the rings for half an SM so that two CTAs can be co-resident (see halo_finish_config)
@@ -433,9 +479,9 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.acc_cols = acc_cols;
   kp.acc_stages = 512 / (S * acc_cols);
   if (kp.acc_stages > kConvMaxAcc) kp.acc_stages = kConvMaxAcc;
-  kp.idesc = umma_idesc_f16(BN, 0);
+  kp.idesc = kp.pair ? umma_idesc_f16_m256(BN) : umma_idesc_f16(BN, 0);
   kp.tiles_w = (kp.Wo + 8 * S - 1) / (8 * S);
-  kp.tiles_h = (kp.Ho + 15) / 16;
+  kp.tiles_h = kp.pair ? (kp.Ho + 31) / 32 : (kp.Ho + 15) / 16;
   kp.tiles_n = kp.N;
   kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
   halo_finish_config(plan);
@@ -458,7 +504,7 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   {
     cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)d->cout_pad, 9};
     cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * d->cout_pad * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kp.KB, (cuuint32_t)BN, (cuuint32_t)G};
+    cuuint32_t box[3] = {(cuuint32_t)kp.KB, (cuuint32_t)(kp.pair ? BN / 2 : BN), (cuuint32_t)G};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&plan->tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d->weight), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -475,7 +521,23 @@ int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
     attr_err = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   PB_CHECK(attr_err == cudaSuccess, "conv(halo): cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
-  conv_halo_kernel<<<plan->grid, plan->threads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->kp);
+  if (plan->kp.pair) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(plan->grid);
+    cfg.blockDim = dim3(plan->threads);
+    cfg.dynamicSmemBytes = plan->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PB_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel, plan->tmap_a, plan->tmap_w, plan->kp));
+  } else {
+    conv_halo_kernel<<<plan->grid, plan->threads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->kp);
+  }
   PB_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -58,6 +58,7 @@ struct ConvKParams {
   uint32_t a_bytes, b_bytes, b_tx_bytes;
   int acc_stages, acc_cols;  // TMEM accumulator ring: acc_stages buffers, acc_cols columns apart
   int tmem_cols;             // TMEM columns allocated by the CTA (power of two; 512 unless two CTAs share an SM)
+  int pair;                  // 1: CTA-pair mode (cluster of 2, cta_group::2 UMMAs issued by the even CTA)
   int egroups;               // epilogue warp groups (2 with 352 threads, 1 with 224 threads / two CTAs per SM)
   const float* head_w;
   const float* head_b;

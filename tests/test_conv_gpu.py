@@ -166,3 +166,23 @@ def test_stem_conv_padded4_layout(shape):
         got = out.cpu().float()[..., :cout].permute(0, 3, 1, 2)
         err = (got - y).abs()
         assert (err > 2e-3 + 2e-3 * y.abs()).float().mean().item() == 0.0, (reference, err.max().item())
+
+
+PAIR_CASES = [
+    dict(N=1, H=32, W=64, cin=64, cout=64, k=3, s=1, act=L.ACT_RELU),
+    dict(N=2, H=48, W=40, cin=64, cout=64, k=3, s=1, act=L.ACT_RELU),             # odd number of 16-row tiles
+    dict(N=1, H=64, W=64, cin=192, cout=64, k=3, s=1, act=L.ACT_RELU),
+    dict(N=2, H=32, W=32, cin=128, cout=128, k=3, s=1, act=L.ACT_SILU, residual=True),
+    dict(N=1, H=32, W=32, cin=32, cout=32, k=3, s=1, act=L.ACT_SILU),
+    dict(N=1, H=32, W=64, cin=64, cout=128, k=3, s=1, act=L.ACT_RELU, out_mode=L.OUT_F16_NHWC_UP2),
+    dict(N=4, H=288, W=512, cin=64, cout=64, k=3, s=1, act=L.ACT_RELU),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_halo_conv_cta_pair_mode(case, monkeypatch):
+    """cta_group::2 variant of the halo kernel: cluster of two CTAs, M=256 UMMAs issued by the even CTA."""
+    monkeypatch.setenv("PADEL_B200_CONV_HALO", "1")
+    monkeypatch.setenv("PADEL_B200_CONV_PAIR", "1")
+    bad, mx = run_case(**case)
+    assert bad == 0.0, f"pair-mode kernel: {bad*100:.3f}% elements out of tolerance (max err {mx})"
