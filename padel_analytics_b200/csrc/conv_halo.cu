@@ -56,6 +56,9 @@ __device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t row_b
          (layout << 61);
 }
 
+// kPair is a compile-time switch: a kernel that contains cta_group::2 instructions can only be launched as a
+// cluster of two, so the single-CTA and the CTA-pair variants are separate instantiations.
+template <bool kPair>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ ConvKParams kp) {
@@ -72,7 +75,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int tap_groups = kp.hs_ntaps / G;
   // CTA-pair mode (cluster of 2, cta_group::2): both CTAs load their own halo and half of the weights, the even
   // CTA issues M=256 UMMAs over both, so every SM reads only half of B from its shared memory.
-  const int pair = kp.pair;
+  constexpr int pair = kPair ? 1 : 0;
   const uint32_t crank = pair ? cluster_ctarank() : 0u;
   const int cta0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int cstride = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -518,7 +521,9 @@ int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   PB_CHECK(attr_err == cudaSuccess, "conv(halo): cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
   if (plan->kp.pair) {
@@ -534,11 +539,20 @@ int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PB_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel, plan->tmap_a, plan->tmap_w, plan->kp));
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<true>, plan->tmap_a, plan->tmap_w, plan->kp);
+    PB_CHECK(le == cudaSuccess, "conv(halo, pair): launch failed: %s (grid %d, threads %d, smem %zu, tiles %d, S %d, BN %d)",
+             cudaGetErrorString(le), plan->grid, plan->threads, plan->smem_bytes, plan->kp.total_tiles, plan->kp.hs_S,
+             plan->kp.BN);
   } else {
-    conv_halo_kernel<<<plan->grid, plan->threads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->kp);
+    conv_halo_kernel<false><<<plan->grid, plan->threads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w,
+                                                                                    plan->kp);
   }
-  PB_CUDA(cudaGetLastError());
+  {
+    cudaError_t le = cudaGetLastError();
+    PB_CHECK(le == cudaSuccess, "conv(halo): launch failed: %s (pair %d, grid %d, threads %d, smem %zu, tiles %d, S %d, BN %d, KB %d)",
+             cudaGetErrorString(le), plan->kp.pair, plan->grid, plan->threads, plan->smem_bytes, plan->kp.total_tiles,
+             plan->kp.hs_S, plan->kp.BN, plan->kp.KB);
+  }
   count_launch();
   return 0;
 }
