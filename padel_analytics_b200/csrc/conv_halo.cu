@@ -176,7 +176,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t aph = 0, bph = 0, acc_ph = 0;
       const int ksteps = kp.KB / 16;
       const uint32_t sbo = (uint32_t)kp.hs_sbo_rows * row_bytes;
-      const uint32_t tap_b_bytes = (uint32_t)(pair ? kp.BN / 2 : kp.BN) * row_bytes;
+      const uint32_t tap_b_units = ((uint32_t)(pair ? kp.BN / 2 : kp.BN) * row_bytes) >> 4;  // 16-byte units
+      const uint64_t sub_units = (uint64_t)((8u * row_bytes) >> 4);                            // next sub-tile: +8 pixels
       for (int tile = cta0; tile < kp.total_tiles; tile += cstride) {
         const int seq = (tile - cta0) / cstride;
         const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
@@ -189,27 +190,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&tail->a_full[ast], aph);
           tc_fence_after();
           if (dbg && cb == 0) kp.dbg[(1 * 64 + seq) * 4 + 2] = clock64();
-          const uint32_t halo = smem_u32(a_base + (size_t)ast * kp.a_bytes);
+          // Descriptor arithmetic is hoisted: per (channel block, weight stage) one base descriptor each; taps,
+          // sub-tiles and k-steps only add precomputed 16-byte-unit offsets to the low word (the single issuing
+          // thread must sustain one UMMA per ~60 cycles, so the inner loop is a handful of instructions).
+          const uint64_t a_desc0 = umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), row_bytes, sbo);
           for (int tg = 0; tg < tap_groups; ++tg) {
             mbar_wait(&tail->b_full[bst], bph);
             tc_fence_after();
-            const uint32_t bsm = smem_u32(b_base + (size_t)bst * kp.b_bytes);
+            const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(b_base + (size_t)bst * kp.b_bytes), row_bytes);
             for (int ti = 0; ti < G; ++ti) {
               const int tap = tg * G + ti;
-              const uint32_t toff = (uint32_t)kp.hs_tap_off[tap];
-              const uint64_t bdesc = umma_desc_kmajor(bsm + (uint32_t)ti * tap_b_bytes, row_bytes);
+              const uint64_t bd = b_desc0 + (uint64_t)((uint32_t)ti * tap_b_units);
+              uint64_t ad = a_desc0 + (uint64_t)(uint32_t)kp.hs_tap_desc[tap];
+              uint32_t dj = d0;
+              const uint32_t first = (uint32_t)((cb | tap) != 0);
               for (int j = 0; j < S; ++j) {
-                const uint64_t adesc = umma_desc_sbo(halo + (toff + 8u * (uint32_t)j) * row_bytes, row_bytes, sbo);
-                const uint32_t dj = d0 + (uint32_t)(j * kp.acc_cols);
-#pragma unroll 4
-                for (int k = 0; k < ksteps; ++k) {
-                  if (pair)
-                    umma_f16_2sm(dj, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kp.idesc,
-                                 (uint32_t)((cb | tap | k) != 0));
-                  else
-                    umma_f16(dj, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kp.idesc,
-                             (uint32_t)((cb | tap | k) != 0));
+                if (kPair) {
+                  umma_f16_2sm(dj, ad, bd, kp.idesc, first);
+                  for (int k = 1; k < ksteps; ++k) umma_f16_2sm(dj, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kp.idesc, 1u);
+                } else {
+                  umma_f16(dj, ad, bd, kp.idesc, first);
+                  for (int k = 1; k < ksteps; ++k) umma_f16(dj, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kp.idesc, 1u);
                 }
+                ad += sub_units;
+                dj += (uint32_t)kp.acc_cols;
               }
             }
             if (pair) umma_commit_2sm(&tail->b_empty[bst]); else umma_commit(&tail->b_empty[bst]);
@@ -362,6 +366,7 @@ int conv_stem_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.hs_x0 = 0;
   kp.hs_y0 = 0;
   for (int r = 0; r < 3; ++r) kp.hs_tap_off[r] = r * 8 * S;
+  for (int r = 0; r < 3; ++r) kp.hs_tap_desc[r] = (kp.hs_tap_off[r] * 32) >> 4;
   kp.BN = BN;
   kp.n_ntiles = 1;
   kp.halo_bytes = 16u * 3u * (uint32_t)(8 * S) * 32u;
@@ -456,7 +461,10 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.hs_x0 = -1;
   kp.hs_y0 = -1;
   for (int r = 0; r < 3; ++r)
-    for (int q = 0; q < 3; ++q) kp.hs_tap_off[r * 3 + q] = r * P + q;
+    for (int q = 0; q < 3; ++q) {
+      kp.hs_tap_off[r * 3 + q] = r * P + q;
+      kp.hs_tap_desc[r * 3 + q] = (int)(((uint32_t)(r * P + q) * row_bytes) >> 4);
+    }
   kp.BN = BN;
   kp.n_ntiles = 1;
   kp.halo_bytes = 18u * (uint32_t)P * row_bytes;

@@ -105,3 +105,71 @@ extern "C" int pb_debug_umma_shift(const void* A /*half [192][64]*/, const void*
   PB_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Micro-benchmark: cycles per UMMA (M=128, K=16, N given) when A comes from shared memory (SS) versus when A is first
+// copied smem -> TMEM with tcgen05.cp.128x256b and the MMA reads it from TMEM (TS).  Decides whether the conv kernels
+// should stage A through TMEM.  One CTA per SM, `iters` back-to-back k-steps on fixed (garbage) operands.
+// ------------------------------------------------------------------------------------------------------------
+namespace pb {
+__global__ void __launch_bounds__(128, 1) debug_umma_rate_kernel(long long* out, int N, int mode, int iters) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 64 * 1024);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tptr, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+  if (threadIdx.x == 0) {
+    const uint32_t a_addr = smem_u32(smem);               // 16 KB: 128 rows x 128 B
+    const uint32_t b_addr = smem_u32(smem + 16 * 1024);   // 32 KB: 256 rows x 128 B
+    const uint64_t adesc = umma_desc_kmajor(a_addr, 128);
+    const uint64_t bdesc = umma_desc_kmajor(b_addr, 128);
+    const uint32_t idesc = umma_idesc_f16(N, 0);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int k = it & 3;
+      if (mode == 0) {
+        umma_f16(tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+      } else {
+        const uint32_t a_t = tmem + 256u + (uint32_t)((it & 7) * 8);  // 8 rotating A buffers of 8 columns
+        asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(a_t), "l"(adesc + (uint64_t)(2 * k)) : "memory");
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem),
+            "r"(a_t), "l"(bdesc + (uint64_t)(2 * k)), "r"(idesc), "r"(1u)
+            : "memory");
+      }
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+}  // namespace pb
+
+extern "C" int pb_debug_umma_rate(long long* out, int N, int mode, int iters, void* stream) {
+  using namespace pb;
+  const size_t smem = 64 * 1024 + 64 + 1024;
+  PB_CUDA(cudaFuncSetAttribute(debug_umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  debug_umma_rate_kernel<<<num_sms(), 128, smem, static_cast<cudaStream_t>(stream)>>>(out, N, mode, iters);
+  PB_CUDA(cudaGetLastError());
+  return 0;
+}

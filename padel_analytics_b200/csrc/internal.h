@@ -68,6 +68,7 @@ struct ConvKParams {
   uint32_t halo_bytes;
   int hs_ntaps, hs_sbo_rows, hs_x0, hs_y0, hs_tile_h;  // taps served from the halo, 8-row group stride (rows), box origin offsets
   int hs_tap_off[9];                                   // smem row offset of each tap's first pixel
+  int hs_tap_desc[9];                                  // the same in 16-byte descriptor units (offset * row_bytes / 16)
   long long* dbg;  // optional timeline buffer (CTA 0, first 64 tiles): [role 0..2][64][4] clock64 stamps
 };
 
