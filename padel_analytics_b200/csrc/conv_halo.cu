@@ -15,6 +15,7 @@
 // Replaces the same reference layers as conv_tc.cu (TrackNet Conv2DBlock models.py:5-17; ultralytics 3x3 convs).
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "conv_common.cuh"
 #include "internal.h"
@@ -58,7 +59,9 @@ __device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t row_b
 
 // kPair is a compile-time switch: a kernel that contains cta_group::2 instructions can only be launched as a
 // cluster of two, so the single-CTA and the CTA-pair variants are separate instantiations.
-template <bool kPair>
+// kS (sub-tiles) and kSteps (16-element k-steps per channel block) are compile-time so the single-thread UMMA issue
+// loop is straight-line code with immediate descriptor offsets.
+template <bool kPair, int kS, int kSteps>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ ConvKParams kp) {
@@ -70,7 +73,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int S = kp.hs_S, G = kp.hs_G;
+  constexpr int S = kS;
+  const int G = kp.hs_G;
   const uint32_t row_bytes = (uint32_t)kp.KB * 2u;
   const int tap_groups = kp.hs_ntaps / G;
   // CTA-pair mode (cluster of 2, cta_group::2): both CTAs load their own halo and half of the weights, the even
@@ -174,10 +178,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0 && crank == 0) {
       int ast = 0, bst = 0, acc = 0;
       uint32_t aph = 0, bph = 0, acc_ph = 0;
-      const int ksteps = kp.KB / 16;
       const uint32_t sbo = (uint32_t)kp.hs_sbo_rows * row_bytes;
       const uint32_t tap_b_units = ((uint32_t)(pair ? kp.BN / 2 : kp.BN) * row_bytes) >> 4;  // 16-byte units
       const uint64_t sub_units = (uint64_t)((8u * row_bytes) >> 4);                            // next sub-tile: +8 pixels
+      const uint32_t acc_cols = (uint32_t)kp.acc_cols;
+      const uint32_t idesc = kp.idesc;
       for (int tile = cta0; tile < kp.total_tiles; tile += cstride) {
         const int seq = (tile - cta0) / cstride;
         const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
@@ -186,34 +191,40 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tc_fence_after();
         if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 1] = clock64();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * S * kp.acc_cols);
+        long long bwait = 0;
         for (int cb = 0; cb < kp.kblocks; ++cb) {
+          const long long ta = dbg ? clock64() : 0;
           mbar_wait(&tail->a_full[ast], aph);
           tc_fence_after();
-          if (dbg && cb == 0) kp.dbg[(1 * 64 + seq) * 4 + 2] = clock64();
+          if (dbg) bwait += clock64() - ta;
           // Descriptor arithmetic is hoisted: per (channel block, weight stage) one base descriptor each; taps,
           // sub-tiles and k-steps only add precomputed 16-byte-unit offsets to the low word (the single issuing
           // thread must sustain one UMMA per ~60 cycles, so the inner loop is a handful of instructions).
           const uint64_t a_desc0 = umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), row_bytes, sbo);
           for (int tg = 0; tg < tap_groups; ++tg) {
+            const long long tb = dbg ? clock64() : 0;
             mbar_wait(&tail->b_full[bst], bph);
             tc_fence_after();
+            if (dbg) bwait += clock64() - tb;
             const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(b_base + (size_t)bst * kp.b_bytes), row_bytes);
             for (int ti = 0; ti < G; ++ti) {
               const int tap = tg * G + ti;
               const uint64_t bd = b_desc0 + (uint64_t)((uint32_t)ti * tap_b_units);
-              uint64_t ad = a_desc0 + (uint64_t)(uint32_t)kp.hs_tap_desc[tap];
-              uint32_t dj = d0;
+              const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)kp.hs_tap_desc[tap];
+              const uint32_t dj = d0;
               const uint32_t first = (uint32_t)((cb | tap) != 0);
-              for (int j = 0; j < S; ++j) {
-                if (kPair) {
-                  umma_f16_2sm(dj, ad, bd, kp.idesc, first);
-                  for (int k = 1; k < ksteps; ++k) umma_f16_2sm(dj, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kp.idesc, 1u);
-                } else {
-                  umma_f16(dj, ad, bd, kp.idesc, first);
-                  for (int k = 1; k < ksteps; ++k) umma_f16(dj, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kp.idesc, 1u);
+#pragma unroll
+              for (int j = 0; j < kS; ++j) {
+#pragma unroll
+                for (int k = 0; k < kSteps; ++k) {
+                  const uint32_t accf = k == 0 ? first : 1u;
+                  if (kPair)
+                    umma_f16_2sm(dj + (uint32_t)j * acc_cols, ad + (uint64_t)j * sub_units + (uint64_t)(2 * k),
+                                 bd + (uint64_t)(2 * k), idesc, accf);
+                  else
+                    umma_f16(dj + (uint32_t)j * acc_cols, ad + (uint64_t)j * sub_units + (uint64_t)(2 * k),
+                             bd + (uint64_t)(2 * k), idesc, accf);
                 }
-                ad += sub_units;
-                dj += (uint32_t)kp.acc_cols;
               }
             }
             if (pair) umma_commit_2sm(&tail->b_empty[bst]); else umma_commit(&tail->b_empty[bst]);
@@ -229,7 +240,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         if (pair) umma_commit_2sm(&tail->tmem_full[acc]); else umma_commit(&tail->tmem_full[acc]);
-        if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 3] = clock64();
+        if (dbg) {
+          kp.dbg[(1 * 64 + seq) * 4 + 2] = bwait;  // cycles this tile spent waiting for operands (a_full + b_full)
+          kp.dbg[(1 * 64 + seq) * 4 + 3] = clock64();
+        }
         if (++acc == kp.acc_stages) {
           acc = 0;
           acc_ph ^= 1;
@@ -525,42 +539,55 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   return 0;
 }
 
+typedef void (*HaloKernelFn)(CUtensorMap, CUtensorMap, ConvKParams);
+
+template <bool kPair>
+static HaloKernelFn halo_kernel_for(int S, int steps) {
+#define PB_HALO_CASE(s_, k_) \
+  if (S == s_ && steps == k_) return conv_halo_kernel<kPair, s_, k_>;
+  PB_HALO_CASE(1, 1) PB_HALO_CASE(1, 2) PB_HALO_CASE(1, 4)
+  PB_HALO_CASE(2, 1) PB_HALO_CASE(2, 2) PB_HALO_CASE(2, 4)
+  PB_HALO_CASE(4, 1) PB_HALO_CASE(4, 2) PB_HALO_CASE(4, 4)
+#undef PB_HALO_CASE
+  return nullptr;
+}
+
 int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  PB_CHECK(attr_err == cudaSuccess, "conv(halo): cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
-  if (plan->kp.pair) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(plan->grid);
-    cfg.blockDim = dim3(plan->threads);
-    cfg.dynamicSmemBytes = plan->smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+  const ConvKParams& kp = plan->kp;
+  HaloKernelFn fn = kp.pair ? halo_kernel_for<true>(kp.hs_S, kp.KB / 16) : halo_kernel_for<false>(kp.hs_S, kp.KB / 16);
+  PB_CHECK(fn != nullptr, "conv(halo): no kernel instantiation for S=%d, k-steps=%d", kp.hs_S, kp.KB / 16);
+  {
+    static std::mutex mu;
+    static std::vector<const void*> configured;
+    std::lock_guard<std::mutex> lk(mu);
+    bool seen = false;
+    for (const void* p : configured) seen = seen || p == reinterpret_cast<const void*>(fn);
+    if (!seen) {
+      PB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+      configured.push_back(reinterpret_cast<const void*>(fn));
+    }
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(plan->grid);
+  cfg.blockDim = dim3(plan->threads);
+  cfg.dynamicSmemBytes = plan->smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (kp.pair) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<true>, plan->tmap_a, plan->tmap_w, plan->kp);
-    PB_CHECK(le == cudaSuccess, "conv(halo, pair): launch failed: %s (grid %d, threads %d, smem %zu, tiles %d, S %d, BN %d)",
-             cudaGetErrorString(le), plan->grid, plan->threads, plan->smem_bytes, plan->kp.total_tiles, plan->kp.hs_S,
-             plan->kp.BN);
-  } else {
-    conv_halo_kernel<false><<<plan->grid, plan->threads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w,
-                                                                                    plan->kp);
   }
-  {
-    cudaError_t le = cudaGetLastError();
-    PB_CHECK(le == cudaSuccess, "conv(halo): launch failed: %s (pair %d, grid %d, threads %d, smem %zu, tiles %d, S %d, BN %d, KB %d)",
-             cudaGetErrorString(le), plan->kp.pair, plan->grid, plan->threads, plan->smem_bytes, plan->kp.total_tiles,
-             plan->kp.hs_S, plan->kp.BN, plan->kp.KB);
-  }
+  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, plan->tmap_a, plan->tmap_w, plan->kp);
+  if (le == cudaSuccess) le = cudaGetLastError();
+  PB_CHECK(le == cudaSuccess,
+           "conv(halo): launch failed: %s (pair %d, grid %d, threads %d, smem %zu, tiles %d, S %d, BN %d, KB %d)",
+           cudaGetErrorString(le), kp.pair, plan->grid, plan->threads, plan->smem_bytes, kp.total_tiles, kp.hs_S, kp.BN,
+           kp.KB);
   count_launch();
   return 0;
 }

@@ -26,10 +26,10 @@ def run(N, H, W, cin, cout, k, s=1, mode=L.OUT_F16_NHWC, act=L.ACT_SILU):
     print("tile | prod start,end | mma start, got-acc, got-full, committed | epi start, got-tmem_full, done")
     for i in list(range(0, 14)) + [30, 31, 32, 33]:
         r = lambda a: int(a) - t0
-        print(f"{i:3d} | {r(t[0,i,0]):7d} {r(t[0,i,1]):7d} | {r(t[1,i,0]):7d} {r(t[1,i,1]):7d} {r(t[1,i,2]):7d} {r(t[1,i,3]):7d} | {r(t[2,i,0]):7d} {r(t[2,i,1]):7d} {r(t[2,i,2]):7d}")
+        print(f"{i:3d} | {r(t[0,i,0]):7d} {r(t[0,i,1]):7d} | {r(t[1,i,0]):7d} {r(t[1,i,1]):7d} {int(t[1,i,2]):7d} {r(t[1,i,3]):7d} | {r(t[2,i,0]):7d} {r(t[2,i,1]):7d} {r(t[2,i,2]):7d}")
 import os
 os.environ["PADEL_B200_CONV_HALO"] = "1"
-print("halo: prod = [tile start, got a_empty] ; mma = [start, got acc, got a_full(cb0), committed] ; epi = [start, got tmem_full, done]")
+print("halo: prod = [tile start, got a_empty] ; mma = [start, got acc, OPERAND-WAIT CYCLES (not a timestamp), committed] ; epi = [start, got tmem_full, done]")
 run(32, 288, 512, 64, 64, 3, act=L.ACT_RELU)
 run(32, 288, 512, 192, 64, 3, act=L.ACT_RELU)
 run(32, 160, 160, 32, 32, 3)
