@@ -29,6 +29,13 @@ __device__ __forceinline__ void bias_act16(const uint32_t (&r)[16], const float*
   }
 }
 
+// 32-byte store (STG.256): one instruction and one full 32-byte sector per 16 fp16 channels
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 struct EpiPix {
   bool valid;
   int n, oh, ow;
@@ -75,10 +82,15 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& kp, const Ep
     for (int j = 0; j < 8; ++j) h2[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
     __half* ob = reinterpret_cast<__half*>(kp.out);
     const bool two = (kp.cout_store - ch0 >= 16);  // cout_store is a multiple of 8
+    const bool wide = two && (((kp.out_C | kp.out_coff) & 15) == 0);  // 32-byte aligned 16-channel run
     if (kp.out_mode == PB_OUT_F16_NHWC) {
       uint4* op = reinterpret_cast<uint4*>(ob + px.pix * kp.out_C + kp.out_coff + ch0);
-      op[0] = pk[0];
-      if (two) op[1] = pk[1];
+      if (wide) {
+        st_global_256(op, pk[0], pk[1]);
+      } else {
+        op[0] = pk[0];
+        if (two) op[1] = pk[1];
+      }
     } else {
       const int Wo2 = kp.Wo * 2;
 #pragma unroll
@@ -87,8 +99,12 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& kp, const Ep
         for (int dx = 0; dx < 2; ++dx) {
           const size_t pix2 = ((size_t)px.n * (kp.Ho * 2) + (px.oh * 2 + dy)) * Wo2 + (px.ow * 2 + dx);
           uint4* op = reinterpret_cast<uint4*>(ob + pix2 * kp.out_C + kp.out_coff + ch0);
-          op[0] = pk[0];
-          if (two) op[1] = pk[1];
+          if (wide) {
+            st_global_256(op, pk[0], pk[1]);
+          } else {
+            op[0] = pk[0];
+            if (two) op[1] = pk[1];
+          }
         }
     }
   } else if (kp.out_mode == PB_OUT_F32_NHWC) {
