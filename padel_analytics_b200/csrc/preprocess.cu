@@ -73,9 +73,11 @@ __global__ void letterbox_kernel(const uint8_t* __restrict__ src, int B, int Hs,
 __global__ void __launch_bounds__(256)
 pil_horizontal_kernel(const uint8_t* __restrict__ src, int Ws, uint8_t* __restrict__ tmp, int Wo,
                       const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, int swap_rb) {
-  extern __shared__ __align__(16) uint8_t hrow[];
+  extern __shared__ __align__(16) uint8_t hrow[];  // [raw row: Ws*3 bytes, 16-aligned][packed row: Ws uint32]
   const size_t row = blockIdx.x;  // b*Hs + y
   const int rowbytes = Ws * 3;
+  const int rawpad = (rowbytes + 15) & ~15;
+  uint32_t* packed = reinterpret_cast<uint32_t*>(hrow + rawpad);
   const uint8_t* g = src + row * (size_t)rowbytes;
   if ((rowbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
     for (int i = threadIdx.x; i < rowbytes / 16; i += blockDim.x)
@@ -84,17 +86,22 @@ pil_horizontal_kernel(const uint8_t* __restrict__ src, int Ws, uint8_t* __restri
     for (int i = threadIdx.x; i < rowbytes; i += blockDim.x) hrow[i] = g[i];
   }
   __syncthreads();
+  // one 32-bit word per pixel (c0 | c1<<8 | c2<<16): a filter tap then costs one shared-memory load, not three
+  for (int x = threadIdx.x; x < Ws; x += blockDim.x)
+    packed[x] = (uint32_t)hrow[3 * x] | ((uint32_t)hrow[3 * x + 1] << 8) | ((uint32_t)hrow[3 * x + 2] << 16);
+  __syncthreads();
   uint8_t* o = tmp + row * (size_t)Wo * 3;
   for (int xo = threadIdx.x; xo < Wo; xo += blockDim.x) {
     const int xmin = bounds[2 * xo], xs = bounds[2 * xo + 1];
     const int* k = kk + (size_t)xo * ksize;
-    const uint8_t* p = hrow + xmin * 3;
+    const uint32_t* p = packed + xmin;
     int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
     for (int x = 0; x < xs; ++x) {
       const int kv = __ldg(k + x);
-      s0 += p[3 * x + 0] * kv;
-      s1 += p[3 * x + 1] * kv;
-      s2 += p[3 * x + 2] * kv;
+      const uint32_t px = p[x];
+      s0 += (int)(px & 0xFF) * kv;
+      s1 += (int)((px >> 8) & 0xFF) * kv;
+      s2 += (int)((px >> 16) & 0xFF) * kv;
     }
     const uint8_t v0 = (uint8_t)min(max(s0 >> 22, 0), 255);
     const uint8_t v1 = (uint8_t)min(max(s1 >> 22, 0), 255);
@@ -260,7 +267,7 @@ int pb_pil_resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* tmp, ui
   PB_CHECK(Wo % 4 == 0, "pil_resize: output width %d must be a multiple of 4", Wo);
   PB_CHECK(f16_layout >= 0 && f16_layout <= 2, "pil_resize: bad f16_layout");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t hsmem = ((size_t)Ws * 3 + 15) & ~(size_t)15;
+  const size_t hsmem = (((size_t)Ws * 3 + 15) & ~(size_t)15) + (size_t)Ws * 4;
   PB_CHECK(hsmem <= 48 * 1024, "pil_resize: source rows of %d pixels do not fit the row buffer", Ws);
   pil_horizontal_kernel<<<B * Hs, 256, hsmem, s>>>(src, Ws, tmp, Wo, bounds_h, kk_h, ksize_h, swap_rb);
   PB_CUDA(cudaGetLastError());
