@@ -155,6 +155,13 @@ int pb_yolo_decode(const pb_yolo_level* levels, int nlevels, int B, int fC, int 
 int pb_yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count, int B, int cap, int rowlen,
                 float iou, int max_det, float* out, int* out_count, void* stream);
 
+/* ---- InpaintNet (ball_tracker/models.py:101-130, called at ball_tracker.py:573-576) ----------------------- */
+/* coor float (N,L,2) normalised coordinates, mask float (N,L) inpaint mask -> out float (N,L,2) = sigmoid(net).
+ * weights: float blob, the nine Conv1d layers in forward order (down_1, down_2, down_3, buttleneck.conv_1,
+ * buttleneck.conv_2, up_1, up_2, up_3, predictor), each as weight [cout][cin][3] followed by bias [cout]. L <= 32. */
+int pb_inpaintnet_forward(const float* coor, const float* mask, int N, int L, const float* weights, float* out,
+                          void* stream);
+
 /* ---- TrackNet post-processing (ball_tracker.py:449-509 ; predict.py:7-39) ---------------------------------- */
 /* Temporal ensemble + >thr. pred: float (S,8,H,W) raw heat-maps of consecutive windows; window index of pred[0]
  * is `first_window`; frames [frame0, frame0+nframes) are produced; total_windows = total_frames-7.

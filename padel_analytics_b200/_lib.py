@@ -63,6 +63,7 @@ SIGNATURES = {
     "pb_tracknet_pack_windows": (_i, [_p, _i, _i, _p, _i, _i, _i, _p, _p]),
     "pb_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _i, _p]),
     "pb_yolo_nms": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p, _p]),
+    "pb_inpaintnet_forward": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "pb_tracknet_ensemble": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p]),
     "pb_ccl_bbox": (_i, [_p, _i, _i, _i, _p, _p, _p]),
 }

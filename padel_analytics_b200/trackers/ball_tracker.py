@@ -7,7 +7,9 @@ Documented deviations from reference quirks:
   q2  when `median` is None the reference buffers the first `median_max_sample_num` frames, converts them BGR->RGB
       twice and restarts the sliding window at the buffer boundary; here the median is computed from the same frames
       but every frame is converted once and the window never restarts.
-  InpaintNet (:525-673) is not on the B200 path yet: passing inpainting_model_path raises.
+  InpaintNet stage (:525-673): supported — the network runs as one fused CUDA kernel (engine/inpaint_engine.py), the
+      surrounding bookkeeping (inpaint mask :100-136, sequence building dataset.py:387-429,493-503, blend, COOR_TH
+      thresholds, coordinate ensemble, predict.py:91-147) is restated on the host in `_inpaint_stage`.
 """
 from __future__ import annotations
 
@@ -18,6 +20,7 @@ from typing import Iterable, Optional, Type
 import numpy as np
 import torch
 
+from ..engine.inpaint_engine import InpaintNetEngine
 from ..engine.tracknet_engine import BallPipeline, TrackNetEngine, bbox_to_xyv
 from .tracker import NoPredictSample, Object, Tracker
 
@@ -92,8 +95,12 @@ class BallTracker(Tracker):
             raise NotImplementedError("only bg_mode='concat' (what predict_frames hard-codes, :403) is supported")
         self.tracknet = TrackNetEngine(ckpt["model"], max_batch=batch_size, height=self.HEIGHT, width=self.WIDTH)
         if inpainting_model_path:
-            raise NotImplementedError("InpaintNet stage is not on the B200 path yet (SURVEY §8f item 1)")
-        self.inpaintnet = None
+            ick = inpainting_model_path if isinstance(inpainting_model_path, dict) else \
+                torch.load(inpainting_model_path, map_location="cpu", weights_only=False)
+            self.inpaintnet_seq_len = ick["param_dict"]["seq_len"]  # ball_tracker.py:270
+            self.inpaintnet = InpaintNetEngine(ick["model"])
+        else:
+            self.inpaintnet = None
         self.batch_size = batch_size
         self.median_max_sample_num = median_max_sample_num
         self.median = median
@@ -222,8 +229,82 @@ class BallTracker(Tracker):
 
         return finish
 
+    # ---- InpaintNet stage (ball_tracker.py:525-673) -------------------------------------------------------------
+    @staticmethod
+    def _generate_inpaint_mask(y, vis, th_h: float):
+        """ball_tracker.py:100-136."""
+        y, vis = np.array(y), np.array(vis)
+        mask = np.zeros_like(y)
+        i = j = 0
+        while j < len(vis):
+            while i < len(vis) - 1 and vis[i] == 1:
+                i += 1
+            j = i
+            while j < len(vis) - 1 and vis[j] == 0:
+                j += 1
+            if j == i:
+                break
+            elif i == 0 and y[j] > th_h:
+                mask[:j] = 1
+            elif (i > 1 and y[i - 1] > th_h) and (j < len(vis) and y[j] > th_h):
+                mask[i:j] = 1
+            i = j
+        return mask
+
+    def _inpaint_stage(self, xs, ys, vs):
+        """TrackNet per-frame (x, y, vis) lists (every frame 0..T-1 present) -> inpainted lists, as the reference does
+        between :525 and :673.  Sequences (stride 1, length L) -> InpaintNet on device -> blend with the mask -> COOR_TH
+        threshold -> temporal ensemble over the L windows covering each frame -> threshold -> pixel coordinates."""
+        Lq = self.inpaintnet_seq_len
+        T = len(xs)
+        W_img, H_img = self.video_info.width, self.video_info.height
+        mask = self._generate_inpaint_mask(ys, vs, th_h=H_img * 0.05)
+        S = T - Lq + 1
+        if S <= 0:
+            return {}
+        sel = np.arange(S)[:, None] + np.arange(Lq)[None, :]
+        coor = np.stack([np.asarray(xs, np.float32)[sel], np.asarray(ys, np.float32)[sel]], -1)  # dataset.py:390-420
+        coor[:, :, 0] = coor[:, :, 0] / W_img  # dataset.py:499-500
+        coor[:, :, 1] = coor[:, :, 1] / H_img
+        m = np.asarray(mask, np.float32)[sel][..., None]
+        c_t, m_t = torch.from_numpy(coor), torch.from_numpy(m)
+        out = self.inpaintnet(c_t, m_t).cpu()
+        out = out * m_t + c_t * (1 - m_t)  # :577
+        th = (out[:, :, 0] < self.COOR_TH) & (out[:, :, 1] < self.COOR_TH)
+        out[th] = 0.0
+        # temporal ensemble on coordinates (:584-652): frame n <- windows n-L+1..n, slot L-1-k of window n-L+1+k
+        w = torch.ones(Lq)
+        for i in range(math.ceil(Lq / 2)):
+            w[i] = i + 1
+            w[Lq - i - 1] = i + 1
+        w = w / w.sum()
+        zero = torch.zeros(2)
+        ens = torch.zeros((T, 2))
+        for n in range(T):
+            terms = torch.stack([out[n - (Lq - 1) + k, Lq - 1 - k] if 0 <= n - (Lq - 1) + k < S else zero
+                                 for k in range(Lq)])
+            if n < S and n >= Lq - 1:
+                ens[n] = (terms * w[:, None]).sum(0)
+            else:
+                ens[n] = terms.sum(0) / ((n + 1) if n < S else (Lq - (n - (S - 1))))
+        th = (ens[:, 0] < self.COOR_TH) & (ens[:, 1] < self.COOR_TH)
+        ens[th] = 0.0
+        scaler = (W_img / self.WIDTH, H_img / self.HEIGHT)
+        res = {}
+        ens_np = ens.numpy()
+        for n in range(T):  # predict.py:125-129 (numpy float32 scalar arithmetic, int() truncation)
+            cx = int(ens_np[n][0] * self.WIDTH * scaler[0])
+            cy = int(ens_np[n][1] * self.HEIGHT * scaler[1])
+            res[n] = (cx, cy, 0 if (cx == 0 and cy == 0) else 1)
+        return res
+
     def predict_frames(self, frame_generator: Iterable[np.ndarray], total_frames: int, **kwargs) -> list[Ball]:
         xyv = self.track_xyv(frame_generator, total_frames)
+        if self.inpaintnet is not None and len(xyv) == total_frames:
+            # the reference feeds every TrackNet prediction (frames 0..T-1) to the inpainting stage
+            order = sorted(xyv)
+            xyv = self._inpaint_stage([xyv[n][0] for n in order], [xyv[n][1] for n in order],
+                                      [xyv[n][2] for n in order])
         balls = []
         for n in range(total_frames):  # ball_tracker.py:675-698 (missing frames -> (0,0), visibility 0)
             if n in xyv:

@@ -70,6 +70,54 @@ def main():
                             net_h=32, net_w=64)
         print("ball_ref:", ens.shape, "visible frames", int(np.sum(cap["vis"])), list(zip(cap["x"], cap["y"]))[:8])
 
+    # ---- InpaintNet stage (ball_tracker.py:525-673): the reference hard-codes .cuda(); redirect it to the CPU ----
+    from oracle import inpaint as OI
+
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    ick = OI.make_inpaintnet()
+    with tempfile.TemporaryDirectory() as td:
+        tpath, ipath = Path(td) / "tracknet.pt", Path(td) / "inpaint.pt"
+        torch.save(ck, tpath)
+        torch.save(ick, ipath)
+
+        # default 288x512 heat-maps (COOR_TH depends on them); the TrackNet outputs are replaced by a crafted trajectory
+        # with gaps so that the inpaint mask, the InpaintNet blend, both thresholds and the ensemble all do real work
+        T, B, H, W = 44, 8, 360, 640
+        frames = synth.make_frames(T, H, W, seed=9)
+        med = synth.make_median(H, W, seed=9).numpy()
+        bt = rbt.BallTracker(str(tpath), str(ipath), batch_size=B, median=med)
+        bt.video_info_post_init(SimpleNamespace(width=W, height=H, fps=30))
+        rng = np.random.default_rng(3)
+        tx = (100 + 11 * np.arange(T) + rng.integers(-3, 4, T)).astype(int)
+        ty = (120 + 60 * np.sin(np.arange(T) / 5.0) + rng.integers(-3, 4, T)).astype(int)
+        tv = np.ones(T, dtype=int)
+        for lo, hi in ((0, 3), (9, 13), (20, 21), (30, 37)):
+            tv[lo:hi] = 0
+        tx[tv == 0] = 0
+        ty[tv == 0] = 0
+        ty[26] = 10  # a visible point above the th_h line next to nothing
+        cursor = {"n": 0}
+        orig = rbt.predict_modified
+
+        def fake(**kw):
+            n = kw["y_pred"].shape[0]
+            lo = cursor["n"]
+            cursor["n"] += n
+            return {"x": tx[lo:lo + n].tolist(), "y": ty[lo:lo + n].tolist(), "visibility": tv[lo:lo + n].tolist()}
+
+        rbt.predict_modified = fake
+        try:
+            balls = bt.predict_frames((f.numpy() for f in frames), total_frames=T)
+        finally:
+            rbt.predict_modified = orig
+        assert len(balls) == T and cursor["n"] == T
+        np.savez_compressed(OUT / "inpaint_ref.npz", x=tx, y=ty, vis=tv,
+                            X=np.array([b.xy[0] for b in balls]), Y=np.array([b.xy[1] for b in balls]),
+                            V=np.array([b.visibility for b in balls]), T=T, B=B, H=H, W=W, seq_len=16,
+                            net_h=288, net_w=512)
+        print("inpaint_ref: tracknet vis", int(tv.sum()), "-> inpainted vis", int(sum(b.visibility for b in balls)),
+              [b.xy for b in balls][:14])
+
     net = TrackNet(27, 8)
     net.load_state_dict(ck["model"])
     net.eval()

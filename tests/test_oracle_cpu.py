@@ -112,3 +112,15 @@ def test_seeded_weights_are_deterministic_and_useful():
     sample = [Image.fromarray(cv2.cvtColor(f, cv2.COLOR_BGR2RGB)).resize((640, 640)) for f in frames]
     res = yolo.predict(sample, conf=0.5, iou=0.7, imgsz=640, max_det=12)
     assert len(res) == 1 and res[0].keypoints.xy.shape[1:] == (12, 2)
+
+
+def test_inpaint_stage_matches_reference_golden():
+    """oracle/inpaint.py against the reference's own BallTracker inpainting pass (tests/golden/inpaint_ref.npz)."""
+    from oracle import inpaint as OI
+
+    g = np.load(GOLD / "inpaint_ref.npz")
+    net = OI.load_inpaintnet(OI.make_inpaintnet())
+    out, mask = OI.inpaint_stage(net, g["x"].tolist(), g["y"].tolist(), g["vis"].tolist(), (int(g["W"]), int(g["H"])),
+                                 int(g["seq_len"]), (int(g["net_h"]), int(g["net_w"])), batch_size=int(g["B"]))
+    assert sum(mask) > 5 and sum(g["vis"].tolist()) < len(mask)  # the mask and the gaps are exercised
+    assert out["X"] == g["X"].tolist() and out["Y"] == g["Y"].tolist() and out["Visibility"] == g["V"].tolist()

@@ -147,3 +147,34 @@ def test_fused_pass_equals_per_tracker_passes():
     for k in got:
         assert json.dumps(got[k]) == json.dumps(seq[k]), k
     assert [ball.get(n, (0.0, 0.0, 0)) for n in range(T)] == seq["ball"]
+
+
+def test_inpaintnet_kernel_and_stage_match_oracle():
+    """InpaintNet fused kernel vs the oracle module, and BallTracker's inpainting stage vs the oracle stage on the
+    trajectory of the reference-generated golden (tests/golden/inpaint_ref.npz)."""
+    from pathlib import Path
+    from oracle import inpaint as OI
+    from padel_analytics_b200.engine.inpaint_engine import InpaintNetEngine
+
+    ick = OI.make_inpaintnet()
+    net = OI.load_inpaintnet(ick)
+    eng = InpaintNetEngine(ick["model"])
+    g = torch.Generator().manual_seed(1)
+    c = torch.rand((37, 16, 2), generator=g)
+    m = (torch.rand((37, 16, 1), generator=g) > 0.6).float()
+    with torch.no_grad():
+        exp = net(c, m)
+    got = eng(c, m).cpu()
+    assert (got - exp).abs().max().item() < 2e-5
+    gold = np.load(Path(__file__).resolve().parent / "golden" / "inpaint_ref.npz")
+    Wv, Hv = int(gold["W"]), int(gold["H"])
+    bt = BallTracker(OW.make_tracknet(), ick, batch_size=4, median=synth.make_median(Hv, Wv).numpy())
+    bt.video_info_post_init(sv.VideoInfo(width=Wv, height=Hv, fps=30.0, total_frames=int(gold["T"])))
+    res = bt._inpaint_stage(gold["x"].tolist(), gold["y"].tolist(), gold["vis"].tolist())
+    X, Y, V = gold["X"].tolist(), gold["Y"].tolist(), gold["V"].tolist()
+    assert [res[n][2] for n in range(len(X))] == V
+    dx = max(abs(res[n][0] - X[n]) for n in range(len(X)))
+    dy = max(abs(res[n][1] - Y[n]) for n in range(len(X)))
+    assert dx <= 1 and dy <= 1, (dx, dy)  # fp32 kernel vs fp32 CPU convs: integer truncation may move one pixel
+    exact = sum(1 for n in range(len(X)) if (res[n][0], res[n][1]) == (X[n], Y[n]))
+    assert exact >= len(X) - 3
