@@ -135,4 +135,106 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& kp, const Ep
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Fast epilogue for the common case (fp16 NHWC slice out, 32-byte aligned 16-channel runs, no fused head):
+// software-pipelined over 16-column chunks -- the tcgen05.ld (and the residual loads) of chunk i+1 are in flight
+// while chunk i is activated, packed and stored -- and across the S sub-tiles of a halo tile.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool epilogue_fast_ok(const ConvKParams& kp) {
+  return kp.out_mode == PB_OUT_F16_NHWC && kp.head_n == 0 && ((kp.out_C | kp.out_coff) & 15) == 0 &&
+         (kp.cout_store & 15) == 0 && (kp.res == nullptr || ((kp.res_C | kp.res_coff) & 7) == 0);
+}
+
+// SiLU on a pair with one reciprocal: 1/(1+ea) = db * r, 1/(1+eb) = da * r, r = 1/(da*db).  The exponent is clamped
+// to 2^60 so the product stays finite; silu(v) for v < -41 is below 1e-16 either way (fp16 zero).
+__device__ __forceinline__ void silu2(float& a, float& b) {
+  const float ea = ex2_approx(fminf(a * -1.4426950408889634f, 60.f));
+  const float eb = ex2_approx(fminf(b * -1.4426950408889634f, 60.f));
+  const float da = 1.f + ea, db = 1.f + eb;
+  const float r = rcp_approx(da * db);
+  a *= db * r;
+  b *= da * r;
+}
+
+__device__ __forceinline__ void epi_chunk(int act, bool has_res, uint32_t (&r)[16], const float* __restrict__ sbias,
+                                          __half* op, const uint4 (&rv)[2], bool valid) {
+  float v[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * q);
+    v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b.x;
+    v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b.y;
+    v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
+    v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
+  }
+  if (act == PB_ACT_SILU) {  // CTA-uniform
+#pragma unroll
+    for (int i = 0; i < 8; ++i) silu2(v[2 * i], v[2 * i + 1]);
+  } else if (act == PB_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == PB_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+  }
+  if (has_res) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&rv[g]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        v[8 * g + 2 * j] += f.x;
+        v[8 * g + 2 * j + 1] += f.y;
+      }
+    }
+  }
+  uint4 pk[2];
+  __half2* h2 = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h2[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+  if (valid) st_global_256(op, pk[0], pk[1]);
+}
+
+// One thread's share of a tile: `S` sub-tiles (accumulator sets `sub_cols` TMEM columns apart, pixels `sub_out` /
+// `sub_res` halves apart in the output / residual tensors), `nch` 16-column chunks each.  valid_mask bit j = the
+// thread's pixel of sub-tile j exists.  op0 / rp0 already point at channel 0 of this N tile.
+__device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, uint32_t t_addr0, int S, uint32_t sub_cols,
+                                              int nch, const float* __restrict__ sbias, __half* op0,
+                                              const __half* rp0, size_t sub_out, size_t sub_res,
+                                              uint32_t valid_mask) {
+  uint32_t ra[16], rb[16];
+  const int act = kp.act;
+  const bool has_res = kp.res != nullptr;
+  int j = 0, c = 0;
+  tmem_ld16(t_addr0, ra);
+#define PB_EPI_STAGE(cur, nxt)                                                                          \
+  {                                                                                                     \
+    int jn = j, cn = c + 1;                                                                             \
+    if (cn == nch) {                                                                                    \
+      cn = 0;                                                                                           \
+      ++jn;                                                                                             \
+    }                                                                                                   \
+    const bool more = jn < S;                                                                           \
+    const bool valid = ((valid_mask >> j) & 1u) != 0;                                                   \
+    uint4 rv[2] = {};                                                                                   \
+    if (has_res && valid) { /* consumed after the activation math of this chunk */                      \
+      const uint4* rp = reinterpret_cast<const uint4*>(rp0 + (size_t)j * sub_res + c * 16);             \
+      rv[0] = __ldg(rp);                                                                                \
+      rv[1] = __ldg(rp + 1);                                                                            \
+    }                                                                                                   \
+    tmem_ld_wait16(cur);                                                                                \
+    if (more) tmem_ld16(t_addr0 + (uint32_t)jn * sub_cols + (uint32_t)(cn * 16), nxt);                  \
+    epi_chunk(act, has_res, cur, sbias + c * 16, op0 + (size_t)j * sub_out + c * 16, rv, valid);        \
+    if (!more) break;                                                                                   \
+    j = jn;                                                                                             \
+    c = cn;                                                                                             \
+  }
+  for (;;) {
+    PB_EPI_STAGE(ra, rb)
+    PB_EPI_STAGE(rb, ra)
+  }
+#undef PB_EPI_STAGE
+}
+
 }  // namespace pb

@@ -44,10 +44,10 @@ struct HaloTile {
 // pair mode: a "tile" is two vertically adjacent 16-row tiles, one per CTA of the pair (crank = 0 / 1)
 __device__ __forceinline__ HaloTile halo_decode(const ConvKParams& kp, int tile, uint32_t crank) {
   HaloTile t;
-  t.tw = tile % kp.tiles_w;
-  const int q = tile / kp.tiles_w;
-  t.th = kp.pair ? (q % kp.tiles_h) * 2 + (int)crank : q % kp.tiles_h;
-  t.n = q / kp.tiles_h;
+  int q, th;
+  fast_divmod(q, t.tw, tile, kp.fd_w);
+  fast_divmod(t.n, th, q, kp.fd_h);
+  t.th = kp.pair ? th * 2 + (int)crank : th;
   return t;
 }
 
@@ -62,7 +62,7 @@ __device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t row_b
 // kS (sub-tiles) and kSteps (16-element k-steps per channel block) are compile-time so the single-thread UMMA issue
 // loop is straight-line code with immediate descriptor offsets.
 template <bool kPair, int kS, int kSteps>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvMaxThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ ConvKParams kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -122,9 +122,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
+      int seq = -1;
       for (int tile = cta0; tile < kp.total_tiles; tile += cstride) {
         const HaloTile t = halo_decode(kp, tile, crank);
-        const int seq = (tile - cta0) / cstride;
+        ++seq;
         const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
         if (dbg) kp.dbg[(0 * 64 + seq) * 4 + 0] = clock64();
         for (int cb = 0; cb < kp.kblocks; ++cb) {
@@ -175,7 +176,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ===================== UMMA issuer (pair mode: the even CTA only) =====================
-    if (lane == 0 && crank == 0) {
+    // All 32 lanes run the loops on warp-uniform values; only the elected lane's tcgen05 instructions take effect.
+    if (crank == 0) {
+      const uint32_t lead = elect_one();
+      const uint32_t tm_base = __shfl_sync(0xffffffffu, tmem_base, 0);
       int ast = 0, bst = 0, acc = 0;
       uint32_t aph = 0, bph = 0, acc_ph = 0;
       const uint32_t sbo = (uint32_t)kp.hs_sbo_rows * row_bytes;
@@ -183,14 +187,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint64_t sub_units = (uint64_t)((8u * row_bytes) >> 4);                            // next sub-tile: +8 pixels
       const uint32_t acc_cols = (uint32_t)kp.acc_cols;
       const uint32_t idesc = kp.idesc;
+      int seq = -1;
       for (int tile = cta0; tile < kp.total_tiles; tile += cstride) {
-        const int seq = (tile - cta0) / cstride;
+        ++seq;
         const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
-        if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 0] = clock64();
+        if (dbg && lane == 0) kp.dbg[(1 * 64 + seq) * 4 + 0] = clock64();
         mbar_wait(&tail->tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
-        if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 1] = clock64();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * S * kp.acc_cols);
+        if (dbg && lane == 0) kp.dbg[(1 * 64 + seq) * 4 + 1] = clock64();
+        const uint32_t d0 = tm_base + (uint32_t)(acc * S * kp.acc_cols);
         long long bwait = 0;
         for (int cb = 0; cb < kp.kblocks; ++cb) {
           const long long ta = dbg ? clock64() : 0;
@@ -198,8 +203,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after();
           if (dbg) bwait += clock64() - ta;
           // Descriptor arithmetic is hoisted: per (channel block, weight stage) one base descriptor each; taps,
-          // sub-tiles and k-steps only add precomputed 16-byte-unit offsets to the low word (the single issuing
-          // thread must sustain one UMMA per ~60 cycles, so the inner loop is a handful of instructions).
+          // sub-tiles and k-steps only add precomputed 16-byte-unit offsets to the low word.
           const uint64_t a_desc0 = umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), row_bytes, sbo);
           for (int tg = 0; tg < tap_groups; ++tg) {
             const long long tb = dbg ? clock64() : 0;
@@ -211,7 +215,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               const int tap = tg * G + ti;
               const uint64_t bd = b_desc0 + (uint64_t)((uint32_t)ti * tap_b_units);
               const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)kp.hs_tap_desc[tap];
-              const uint32_t dj = d0;
               const uint32_t first = (uint32_t)((cb | tap) != 0);
 #pragma unroll
               for (int j = 0; j < kS; ++j) {
@@ -219,28 +222,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int k = 0; k < kSteps; ++k) {
                   const uint32_t accf = k == 0 ? first : 1u;
                   if (kPair)
-                    umma_f16_2sm(dj + (uint32_t)j * acc_cols, ad + (uint64_t)j * sub_units + (uint64_t)(2 * k),
-                                 bd + (uint64_t)(2 * k), idesc, accf);
+                    umma_f16_2sm_p(d0 + (uint32_t)j * acc_cols, ad + (uint64_t)j * sub_units + (uint64_t)(2 * k),
+                                   bd + (uint64_t)(2 * k), idesc, accf, lead);
                   else
-                    umma_f16(dj + (uint32_t)j * acc_cols, ad + (uint64_t)j * sub_units + (uint64_t)(2 * k),
-                             bd + (uint64_t)(2 * k), idesc, accf);
+                    umma_f16_p(d0 + (uint32_t)j * acc_cols, ad + (uint64_t)j * sub_units + (uint64_t)(2 * k),
+                               bd + (uint64_t)(2 * k), idesc, accf, lead);
                 }
               }
             }
-            if (pair) umma_commit_2sm(&tail->b_empty[bst]); else umma_commit(&tail->b_empty[bst]);
+            if (pair) umma_commit_2sm_p(&tail->b_empty[bst], lead); else umma_commit_p(&tail->b_empty[bst], lead);
             if (++bst == kp.b_stages) {
               bst = 0;
               bph ^= 1;
             }
           }
-          if (pair) umma_commit_2sm(&tail->a_empty[ast]); else umma_commit(&tail->a_empty[ast]);
+          if (pair) umma_commit_2sm_p(&tail->a_empty[ast], lead); else umma_commit_p(&tail->a_empty[ast], lead);
           if (++ast == kp.a_stages) {
             ast = 0;
             aph ^= 1;
           }
         }
-        if (pair) umma_commit_2sm(&tail->tmem_full[acc]); else umma_commit(&tail->tmem_full[acc]);
-        if (dbg) {
+        if (pair) umma_commit_2sm_p(&tail->tmem_full[acc], lead); else umma_commit_p(&tail->tmem_full[acc], lead);
+        if (dbg && lane == 0) {
           kp.dbg[(1 * 64 + seq) * 4 + 2] = bwait;  // cycles this tile spent waiting for operands (a_full + b_full)
           kp.dbg[(1 * 64 + seq) * 4 + 3] = clock64();
         }
@@ -253,20 +256,32 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncwarp();
   } else {
     // ===== epilogue: two groups of 4 warps (2-5, 7-10) alternating tiles; S sub-tiles of 16 rows x 8 columns each
-    const int egroup = warp >= 7 ? 1 : 0;
+    const int egroup = warp >= 7 ? 1 + ((warp - 7) >> 2) : 0;
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const int row = m >> 3, col = m & 7;
-    for (int tile = cta0 + egroup * cstride; tile < kp.total_tiles; tile += kp.egroups * cstride) {
+    const bool fast = epilogue_fast_ok(kp);
+    int seq = egroup, acc = egroup;  // sequence number / accumulator stage / phase by counters (egroups <= acc_stages)
+    uint32_t acc_ph = 0;
+    for (int tile = cta0 + egroup * cstride; egroup < kp.egroups && tile < kp.total_tiles;
+         tile += kp.egroups * cstride, seq += kp.egroups) {
       const HaloTile t = halo_decode(kp, tile, crank);
-      const int seq = (tile - cta0) / cstride;
-      const int acc = seq % kp.acc_stages;
-      const uint32_t acc_ph = (uint32_t)(seq / kp.acc_stages) & 1u;
-      const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64 && (threadIdx.x == 64 || threadIdx.x == 224);
+      const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64 && (threadIdx.x == 64 || (threadIdx.x >= 224 && ((threadIdx.x - 224) & 127) == 0));
       if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 0] = clock64();
       mbar_wait(&tail->tmem_full[acc], acc_ph);
       tc_fence_after();
       if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 1] = clock64();
+      if (fast) {
+        const int oh = t.th * 16 + row, ow0 = t.tw * 8 * S + col;
+        uint32_t vm = 0;
+#pragma unroll
+        for (int j = 0; j < S; ++j) vm |= (uint32_t)((ow0 + 8 * j < kp.Wo) && (oh < kp.Ho)) << j;
+        const size_t pix0 = ((size_t)t.n * kp.Ho + oh) * kp.Wo + ow0;
+        epilogue_fast(kp, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * kp.acc_cols), S,
+                               (uint32_t)kp.acc_cols, kp.cout_store >> 4, tail->bias,
+                               reinterpret_cast<__half*>(kp.out) + pix0 * kp.out_C + kp.out_coff,
+                               kp.res + pix0 * kp.res_C + kp.res_coff, (size_t)8 * kp.out_C, (size_t)8 * kp.res_C, vm);
+      } else
       for (int j = 0; j < S; ++j) {
         EpiPix px;
         px.n = t.n;
@@ -309,6 +324,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         else mbar_arrive(&tail->tmem_empty[acc]);
       }
       if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 2] = clock64();
+      acc += kp.egroups;
+      if (acc >= kp.acc_stages) {
+        acc -= kp.acc_stages;
+        acc_ph ^= 1u;
+      }
     }
   }
 
@@ -346,8 +366,8 @@ static void halo_finish_config(ConvPlan* plan) {
   } else {
     if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
     kp.tmem_cols = 512;
-    kp.egroups = 2;
-    plan->threads = kConvThreads;
+    kp.egroups = kp.pair ? 2 : conv_pick_egroups(kp.acc_stages);
+    plan->threads = conv_threads_for(kp.egroups);
     plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
     if (kp.pair) {  // total_tiles counts pair tiles: two CTAs each
       const int pairs = kp.total_tiles < num_sms() / 2 ? kp.total_tiles : num_sms() / 2;

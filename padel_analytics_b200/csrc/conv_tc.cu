@@ -39,17 +39,14 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& kp, int tile) {
   TileCoord c;
-  int t = tile;
-  c.nt = t % kp.n_ntiles;
-  t /= kp.n_ntiles;
-  c.tw = t % kp.tiles_w;
-  t /= kp.tiles_w;
-  c.th = t % kp.tiles_h;
-  c.tn = t / kp.tiles_h;
+  int t;
+  fast_divmod(t, c.nt, tile, kp.fd_nt);
+  fast_divmod(t, c.tw, t, kp.fd_w);
+  fast_divmod(c.tn, c.th, t, kp.fd_h);
   return c;
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ ConvKParams kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -92,9 +89,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       const int TW = 1 << kp.tw_log2, TH = 1 << kp.th_log2;
       const int TN = 128 >> (kp.tw_log2 + kp.th_log2);
+      int seq = -1;
       for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(kp, tile);
-        const int seq = (tile - blockIdx.x) / gridDim.x;
+        ++seq;
         const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
         if (dbg) kp.dbg[(0 * 64 + seq) * 4 + 0] = clock64();
         for (int tap = 0; tap < kp.taps; ++tap) {
@@ -122,7 +120,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
-        const int nt = tile % kp.n_ntiles;
+        int nt, tq;
+        fast_divmod(tq, nt, tile, kp.fd_nt);
         for (int tap = 0; tap < kp.taps; ++tap) {
           for (int kb = 0; kb < kp.kblocks; ++kb) {
             mbar_wait(&tail->empty[stage], phase ^ 1);
@@ -140,21 +139,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ============================== UMMA issuer ==============================
-    if (lane == 0) {
+    // All 32 lanes run the loop on warp-uniform values (descriptors stay in uniform registers); only the elected
+    // lane's tcgen05 instructions take effect.
+    {
+      const uint32_t lead = elect_one();
+      const uint32_t tm_base = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t swz = (uint32_t)kp.KB * 2u;
       const int ksteps = kp.KB / 16;
+      int seq = -1;
       for (int tile = blockIdx.x; tile < kp.total_tiles; tile += gridDim.x) {
-        const int seq = (tile - blockIdx.x) / gridDim.x;
-        const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64;
+        ++seq;
+        const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64 && lane == 0;
         if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 0] = clock64();
         mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 1] = clock64();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kp.acc_cols);
+        const uint32_t d_tmem = tm_base + (uint32_t)(acc * kp.acc_cols);
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&tail->full[stage], phase);
           tc_fence_after();
@@ -166,16 +170,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll 4
           for (int k = 0; k < ksteps; ++k) {
             // advance 16 K-elements = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kp.idesc,
-                     (uint32_t)((it | k) != 0));
+            umma_f16_p(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kp.idesc,
+                       (uint32_t)((it | k) != 0), lead);
           }
-          umma_commit(&tail->empty[stage]);  // frees the smem slot when these MMAs retire
+          umma_commit_p(&tail->empty[stage], lead);  // frees the smem slot when these MMAs retire
           if (++stage == kp.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tail->tmem_full[acc]);  // accumulator ready for the epilogue
+        umma_commit_p(&tail->tmem_full[acc], lead);  // accumulator ready for the epilogue
         if (dbg) kp.dbg[(1 * 64 + seq) * 4 + 3] = clock64();
         if (++acc == kp.acc_stages) {
           acc = 0;
@@ -186,17 +190,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncwarp();
   } else {
     // ============ epilogue: two groups of 4 warps (2-5 and 7-10), alternating tiles; one TMEM lane quarter per warp
-    const int egroup = warp >= 7 ? 1 : 0;
+    const int egroup = warp >= 7 ? 1 + ((warp - 7) >> 2) : 0;
     const int quarter = warp & 3;
     const int p = quarter * 32 + lane;  // row of the M=128 tile handled by this thread
     const int TWm = (1 << kp.tw_log2) - 1, THm = (1 << kp.th_log2) - 1;
     const int tw_i = p & TWm;
     const int th_i = (p >> kp.tw_log2) & THm;
     const int tn_i = p >> (kp.tw_log2 + kp.th_log2);
-    for (int tile = blockIdx.x + egroup * gridDim.x; tile < kp.total_tiles; tile += kp.egroups * gridDim.x) {
-      const int seq = (tile - blockIdx.x) / gridDim.x;  // per-CTA tile sequence number
-      const int acc = seq % kp.acc_stages;
-      const uint32_t acc_phase = (uint32_t)(seq / kp.acc_stages) & 1u;
+    const bool fast = epilogue_fast_ok(kp);
+    // per-CTA tile sequence number / accumulator stage / phase advance by counters (egroups <= acc_stages)
+    int seq = egroup, acc = egroup;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x + egroup * gridDim.x; egroup < kp.egroups && tile < kp.total_tiles;
+         tile += kp.egroups * gridDim.x, seq += kp.egroups) {
       const TileCoord tc = decode_tile(kp, tile);
       EpiPix px;
       px.ow = (tc.tw << kp.tw_log2) + tw_i;
@@ -204,7 +210,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       px.n = tc.tn * (128 >> (kp.tw_log2 + kp.th_log2)) + tn_i;
       px.valid = (px.ow < kp.Wo) && (px.oh < kp.Ho) && (px.n < kp.N);
       px.pix = ((size_t)px.n * kp.Ho + px.oh) * kp.Wo + px.ow;
-      const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64 && (threadIdx.x == 64 || threadIdx.x == 224);
+      const bool dbg = kp.dbg != nullptr && blockIdx.x == 0 && seq < 64 && (threadIdx.x == 64 || (threadIdx.x >= 224 && ((threadIdx.x - 224) & 127) == 0));
       if (dbg) kp.dbg[(2 * 64 + seq) * 4 + 0] = clock64();
       mbar_wait(&tail->tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -212,6 +218,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kp.acc_cols);
       float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // fused 1x1 head partial sums
       const float* sb = tail->bias + tc.nt * kp.BN;
+      if (fast) {
+        int nch = kp.cout_store - tc.nt * kp.BN;
+        nch = (nch < kp.BN ? nch : kp.BN) >> 4;
+        if (nch > 0)
+          epilogue_fast(kp, t_addr, 1, 0u, nch, sb,
+                                 reinterpret_cast<__half*>(kp.out) + px.pix * kp.out_C + kp.out_coff + tc.nt * kp.BN,
+                                 kp.res + px.pix * kp.res_C + kp.res_coff + tc.nt * kp.BN, 0, 0, px.valid ? 1u : 0u);
+      } else
       for (int c = 0; c < kp.BN; c += 32) {
         // two 16-column TMEM loads in flight, one wait
         uint32_t r0[16], r1[16];
@@ -241,6 +255,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (j < kp.head_n) ho[(size_t)j * plane] = __fdividef(1.f, 1.f + __expf(-(hacc[j] + __ldg(kp.head_b + j))));
+      }
+      acc += kp.egroups;
+      if (acc >= kp.acc_stages) {
+        acc -= kp.acc_stages;
+        acc_phase ^= 1u;
       }
     }
   }
@@ -278,7 +297,7 @@ static int ilog2(int v) {
 static long long* g_conv_dbg = nullptr;  // set through pb_debug_conv_timeline (bring-up only)
 extern "C" void pb_debug_conv_timeline(long long* buf) { g_conv_dbg = buf; }
 
-int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
+static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
   PB_CHECK(d && plan, "conv: null argument");
   PB_CHECK(d->in_layout == PB_IN_NHWC || d->in_layout == PB_IN_STEM4, "conv: bad in_layout");
   const bool stem = d->in_layout == PB_IN_STEM4;
@@ -434,8 +453,8 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
   } else {
     if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // force 1 CTA/SM (TMEM: 512 cols)
     kp.tmem_cols = 512;
-    kp.egroups = 2;
-    plan->threads = kConvThreads;
+    kp.egroups = conv_pick_egroups(kp.acc_stages);
+    plan->threads = conv_threads_for(kp.egroups);
     plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
   }
 
@@ -473,6 +492,16 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
     PB_CHECK(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
   }
   return 0;
+}
+
+int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
+  const int rc = conv_plan_build_impl(d, plan);
+  if (rc == 0) {
+    plan->kp.fd_w = make_fastdiv(plan->kp.tiles_w);
+    plan->kp.fd_h = make_fastdiv(plan->kp.tiles_h);
+    plan->kp.fd_nt = make_fastdiv(plan->kp.n_ntiles);
+  }
+  return rc;
 }
 
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {

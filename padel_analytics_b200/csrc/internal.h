@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <string>
 
@@ -38,12 +39,50 @@ int num_sms();
 // ---- conv plan (built once per layer; holds TMA descriptors + launch geometry) -------------------------------
 constexpr int kConvMaxStages = 12;
 constexpr int kConvMaxAcc = 8;
-constexpr int kConvThreads = 352;  // w0: TMA-A, w1: UMMA issuer, w2-5: epilogue group 0, w6: TMA-B, w7-10: epilogue group 1
+// Warp roles of the conv kernels: w0 TMA-A, w1 UMMA issuer, w2-5 epilogue group 0, w6 TMA-B, then 4 warps per further
+// epilogue group (w7-10, w11-14).  Epilogue groups take tiles round-robin; more groups = more warps to hide the
+// dependent-issue latency of the activation math (ncu: the epilogue warps issue ~20% of the time each).  Three groups
+// = 480 threads is the most that keeps 128 registers per thread (19 warps would be capped at 96).
+constexpr int kConvThreads = 352;     // two groups
+constexpr int kConvMaxThreads = 480;  // three groups
+inline int conv_threads_for(int egroups) { return (7 + 4 * (egroups - 1)) * 32; }
+// groups for a 1-CTA-per-SM launch: at most one per accumulator stage (a group may only wait one phase ahead)
+inline int conv_pick_egroups(int acc_stages) {
+  const char* e = getenv("PADEL_B200_CONV_EGROUPS");
+  int want = e ? atoi(e) : 3;
+  if (want < 1 || want > 3) want = 3;
+  if (want > acc_stages) want = acc_stages;
+  return want < 1 ? 1 : want;
+}
 constexpr int kConvMaxCout = 1024;
+
+// Division by a launch-time constant as multiply-high + shift (dividend < 2^31): the per-tile coordinate decode of the
+// persistent kernels would otherwise spend ~25 instructions per runtime `/` or `%` in every warp, every tile.
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f{(uint32_t)d, 0u, 0u};
+  if (d > 1) {
+    int lg = 0;
+    while ((1u << lg) < (uint32_t)d) ++lg;  // ceil(log2 d)
+    const int p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + (uint32_t)d - 1) / (uint32_t)d);
+    f.shr = (uint32_t)(p - 32);
+  }
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void fast_divmod(int& q, int& r, int n, const FastDiv& f) {
+  q = f.d != 1u ? (int)(__umulhi((uint32_t)n, f.mul) >> f.shr) : n;
+  r = n - q * (int)f.d;
+}
+#endif
 
 struct ConvKParams {
   int N, Ho, Wo;
   int tiles_w, tiles_h, tiles_n, n_ntiles, total_tiles;
+  FastDiv fd_w, fd_h, fd_nt;  // dividers by tiles_w, tiles_h, n_ntiles
   int tw_log2, th_log2;  // TW*TH*TN == 128
   int taps, kblocks, KB, BN, stages, cout_pad;
   int c_in_off;
@@ -59,7 +98,7 @@ struct ConvKParams {
   int acc_stages, acc_cols;  // TMEM accumulator ring: acc_stages buffers, acc_cols columns apart
   int tmem_cols;             // TMEM columns allocated by the CTA (power of two; 512 unless two CTAs share an SM)
   int pair;                  // 1: CTA-pair mode (cluster of 2, cta_group::2 UMMAs issued by the even CTA)
-  int egroups;               // epilogue warp groups (2 with 352 threads, 1 with 224 threads / two CTAs per SM)
+  int egroups;               // epilogue warp groups (1 with 224 threads / two CTAs per SM, else 2 or 4)
   const float* head_w;
   const float* head_b;
   int head_n;

@@ -6,6 +6,7 @@ The drawing / data-collection pass (runner.py:91-173) is outside the hot path an
 from __future__ import annotations
 
 import timeit
+import os
 from typing import Callable, Iterable, Optional
 
 import numpy as np
@@ -35,11 +36,18 @@ class FusedPass:
     the video once per tracker, runner.py:185-234).  Per batch: the next batch's host->device copy
     runs on a copy stream while this batch computes; the four trackers' device work is enqueued back to back without
     host synchronisation, and each tracker's host post-processing (ByteTrack, result objects) overlaps with the device
-    work of the trackers behind it."""
+    work of the trackers behind it.
+
+    `streams` (default env PADEL_B200_STREAMS, else 1): 0 = every tracker on the caller's stream; 1 = the YOLO trackers
+    each on their own stream (their layers are small and latency-bound at batch 32 — many launch fewer CTAs than there
+    are SMs — so three independent chains fill the machine), the ball tracker after them on the caller's stream;
+    2 = all trackers concurrent.  The kernels and their inputs are the same in every mode, so are the results."""
 
     def __init__(self, trackers: dict[str, Tracker], frame_hw: tuple[int, int], batch_size: int, total_frames: int,
-                 first_frame: int = 0, emit_range: Optional[tuple[int, int]] = None):
+                 first_frame: int = 0, emit_range: Optional[tuple[int, int]] = None, streams: Optional[int] = None):
         self.trackers = trackers
+        self.mode = int(os.environ.get("PADEL_B200_STREAMS", "1")) if streams is None else streams
+        self.side = {name: torch.cuda.Stream() for name in trackers}
         self.hw = tuple(frame_hw)
         self.B = batch_size
         self.dev = torch.device("cuda")
@@ -64,13 +72,32 @@ class FusedPass:
 
     def _process(self, fr: torch.Tensor) -> dict:
         pending = []
-        for name, t in self.trackers.items():  # enqueue everything first ...
-            if isinstance(t, BallTracker):
-                pending.append((name, t, t.stream_push_async(fr)))
-            elif getattr(t, "fixed_keypoints_detection", None) is not None:
+        main = torch.cuda.current_stream()
+        forked = []
+        order = list(self.trackers.items())
+        if self.mode == 1:  # YOLO chains first (concurrent), the ball tracker joins behind them
+            order.sort(key=lambda kv: isinstance(kv[1], BallTracker))
+        for name, t in order:  # enqueue everything first ...
+            if getattr(t, "fixed_keypoints_detection", None) is not None:
                 pending.append((name, t, None))
+                continue
+            is_ball = isinstance(t, BallTracker)
+            own = self.mode == 2 or (self.mode == 1 and not is_ball)
+            if own:
+                s = self.side[name]
+                s.wait_stream(main)
+                forked.append(s)
+                ctx = torch.cuda.stream(s)
             else:
-                pending.append((name, t, t.detect_sample_async(fr)))
+                if self.mode == 1:
+                    for s in forked:
+                        main.wait_stream(s)
+                ctx = torch.cuda.stream(main)
+            with ctx:
+                pending.append((name, t, t.stream_push_async(fr) if is_ball else t.detect_sample_async(fr)))
+        for s in forked:  # the caller's stream (and the next upload into this staging slot) follows all of them
+            main.wait_stream(s)
+        pending.sort(key=lambda p: list(self.trackers).index(p[0]))
         out = {}
         for name, t, fin in pending:  # ... then finish in the same order
             if isinstance(t, BallTracker):

@@ -136,17 +136,20 @@ def test_fused_pass_equals_per_tracker_passes():
         seq[k] = [o.serialize() for o in tr[k].predict_and_update(iter(fr)).predictions]
         tr[k].restart()
     seq["ball"] = [(b.xy[0], b.xy[1], b.visibility) for b in tr["ball"].predict_frames(iter(fr), total_frames=T)]
-    fused = FusedPass(tr, (H, W), B, total_frames=T)
     host = frames.pin_memory()
-    got = {k: [] for k in ("players", "pose", "court")}
-    ball = {}
-    for out in fused.run(host[i:i + B] for i in range(0, T, B)):
+    for mode in (0, 1, 2):  # single stream / YOLO chains concurrent / everything concurrent
+        for k in ("players", "pose", "court"):
+            tr[k].restart()
+        fused = FusedPass(tr, (H, W), B, total_frames=T, streams=mode)
+        got = {k: [] for k in ("players", "pose", "court")}
+        ball = {}
+        for out in fused.run(host[i:i + B] for i in range(0, T, B)):
+            for k in got:
+                got[k] += [o.serialize() for o in out[k]]
+            ball.update(out["ball"])
         for k in got:
-            got[k] += [o.serialize() for o in out[k]]
-        ball.update(out["ball"])
-    for k in got:
-        assert json.dumps(got[k]) == json.dumps(seq[k]), k
-    assert [ball.get(n, (0.0, 0.0, 0)) for n in range(T)] == seq["ball"]
+            assert json.dumps(got[k]) == json.dumps(seq[k]), (k, mode)
+        assert [ball.get(n, (0.0, 0.0, 0)) for n in range(T)] == seq["ball"], mode
 
 
 def test_inpaintnet_kernel_and_stage_match_oracle():
