@@ -95,46 +95,66 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(__half* __restrict__ buf
 }
 
 // TrackNet predictor: 1x1 conv (C -> n_out <= 8) + bias + sigmoid, fp16 NHWC in, fp32 NCHW planes out
-// (/root/reference/trackers/ball_tracker/models.py:55,72-73).  HBM-bound: one thread per pixel reads its C channels
-// with 16-byte loads; the tiny weight matrix is broadcast from shared memory; plane writes are coalesced.
-__global__ void __launch_bounds__(256) pointwise_head_kernel(const __half* __restrict__ in, long npix, int C,
-                                                             const float* __restrict__ w, const float* __restrict__ b,
-                                                             int n_out, float* __restrict__ out, int HW) {
-  extern __shared__ float hw_s[];  // [n_out][C] + [n_out]
+// (/root/reference/trackers/ball_tracker/models.py:55,72-73).  HBM-bound (C*2 bytes in, n_out*4 bytes out per pixel):
+// a block stages 256 pixels x C halves in shared memory with fully coalesced 16-byte loads (consecutive threads read
+// consecutive chunks of the NHWC stream), rows padded by 16 bytes so that the per-pixel 16-byte reads that follow are
+// bank-conflict free; each thread then owns one pixel; the tiny weight matrix is broadcast from shared memory and the
+// plane writes are coalesced.
+constexpr int kHeadPix = 256;
+__global__ void __launch_bounds__(kHeadPix) pointwise_head_kernel(const __half* __restrict__ in, long npix, int C,
+                                                                  const float* __restrict__ w,
+                                                                  const float* __restrict__ b, int n_out,
+                                                                  float* __restrict__ out, int HW) {
+  extern __shared__ __align__(16) unsigned char head_smem[];
+  float* hw_s = reinterpret_cast<float*>(head_smem);  // [n_out][C] + [n_out] (+ pad to 16 bytes)
+  const int wfloats = (n_out * C + n_out + 3) & ~3;
+  uint4* rows = reinterpret_cast<uint4*>(hw_s + wfloats);  // [kHeadPix][C/8 + 1]
+  const int cpp = C / 8, pitch = cpp + 1;
   for (int i = threadIdx.x; i < n_out * C; i += blockDim.x) hw_s[i] = w[i];
   for (int i = threadIdx.x; i < n_out; i += blockDim.x) hw_s[n_out * C + i] = b[i];
-  __syncthreads();
-  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < npix; p += (long)gridDim.x * blockDim.x) {
-    float acc[8];
+  for (long p0 = (long)blockIdx.x * kHeadPix; p0 < npix; p0 += (long)gridDim.x * kHeadPix) {
+    __syncthreads();  // weights staged / previous tile consumed
+    const long left = npix - p0;
+    const int npx = left < kHeadPix ? (int)left : kHeadPix;
+    const uint4* src = reinterpret_cast<const uint4*>(in + p0 * C);
+    for (int i = threadIdx.x; i < npx * cpp; i += blockDim.x) {
+      const int px = i / cpp, part = i - px * cpp;
+      rows[px * pitch + part] = __ldg(src + i);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < npx) {
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = (j < n_out) ? hw_s[n_out * C + j] : 0.f;
-    const uint4* ip = reinterpret_cast<const uint4*>(in + p * C);
-    for (int c8 = 0; c8 < C / 8; ++c8) {
-      const uint4 v = __ldg(ip + c8);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-      float x[8];
+      for (int j = 0; j < 8; ++j) acc[j] = (j < n_out) ? hw_s[n_out * C + j] : 0.f;
+      const uint4* ip = rows + threadIdx.x * pitch;
+      for (int c8 = 0; c8 < cpp; ++c8) {
+        const uint4 v = ip[c8];
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+        float x[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 f = __half22float2(h2[q]);
-        x[2 * q] = f.x;
-        x[2 * q + 1] = f.y;
-      }
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __half22float2(h2[q]);
+          x[2 * q] = f.x;
+          x[2 * q + 1] = f.y;
+        }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < n_out) {
-          const float4 wa = *reinterpret_cast<const float4*>(hw_s + j * C + c8 * 8);
-          const float4 wb = *reinterpret_cast<const float4*>(hw_s + j * C + c8 * 8 + 4);
-          acc[j] = fmaf(wa.x, x[0], fmaf(wa.y, x[1], fmaf(wa.z, x[2], fmaf(wa.w, x[3], acc[j]))));
-          acc[j] = fmaf(wb.x, x[4], fmaf(wb.y, x[5], fmaf(wb.z, x[6], fmaf(wb.w, x[7], acc[j]))));
+        for (int j = 0; j < 8; ++j) {
+          if (j < n_out) {
+            const float4 wa = *reinterpret_cast<const float4*>(hw_s + j * C + c8 * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(hw_s + j * C + c8 * 8 + 4);
+            acc[j] = fmaf(wa.x, x[0], fmaf(wa.y, x[1], fmaf(wa.z, x[2], fmaf(wa.w, x[3], acc[j]))));
+            acc[j] = fmaf(wb.x, x[4], fmaf(wb.y, x[5], fmaf(wb.z, x[6], fmaf(wb.w, x[7], acc[j]))));
+          }
         }
       }
-    }
-    const long n = p / HW;
-    const int pix = (int)(p - n * HW);
-    float* o = out + n * (long)n_out * HW + pix;
+      const long p = p0 + threadIdx.x;
+      const long n = p / HW;
+      const int pix = (int)(p - n * HW);
+      float* o = out + n * (long)n_out * HW + pix;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < n_out) o[(long)j * HW] = 1.f / (1.f + __expf(-acc[j]));
+      for (int j = 0; j < 8; ++j)
+        if (j < n_out) o[(long)j * HW] = 1.f / (1.f + __expf(-acc[j]));
+    }
   }
 }
 
@@ -176,9 +196,19 @@ int launch_pointwise_head(const void* in, int N, int H, int W, int C, const floa
   PB_CHECK(in && w && b && out, "pointwise_head: null pointer");
   PB_CHECK(C % 8 == 0 && n_out >= 1 && n_out <= 8, "pointwise_head: C %% 8 == 0 and n_out <= 8 required");
   const long npix = (long)N * H * W;
-  const size_t smem = (size_t)(n_out * C + n_out) * sizeof(float);
-  pointwise_head_kernel<<<grid_for(npix, 256), 256, smem, st>>>(reinterpret_cast<const __half*>(in), npix, C, w, b,
-                                                               n_out, out, H * W);
+  const size_t wfloats = (size_t)((n_out * C + n_out + 3) & ~3);
+  const size_t smem = wfloats * sizeof(float) + (size_t)kHeadPix * (C / 8 + 1) * sizeof(uint4);
+  PB_CHECK(smem <= 96 * 1024, "pointwise_head: C = %d too wide for the staged tile", C);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    PB_CUDA(cudaFuncSetAttribute(pointwise_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  long blocks = (npix + kHeadPix - 1) / kHeadPix;
+  const long cap = (long)num_sms() * 5;
+  if (blocks > cap) blocks = cap;
+  pointwise_head_kernel<<<(int)blocks, kHeadPix, smem, st>>>(reinterpret_cast<const __half*>(in), npix, C, w, b, n_out,
+                                                            out, H * W);
   PB_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -141,12 +141,19 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& kp, const Ep
 // while chunk i is activated, packed and stored -- and across the S sub-tiles of a halo tile.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool epilogue_fast_ok(const ConvKParams& kp) {
-  return kp.out_mode == PB_OUT_F16_NHWC && kp.head_n == 0 && ((kp.out_C | kp.out_coff) & 15) == 0 &&
-         (kp.cout_store & 15) == 0 && (kp.res == nullptr || ((kp.res_C | kp.res_coff) & 7) == 0);
+  if ((kp.dbg_flags & 2) != 0) return false;
+  if (kp.head_n != 0 || (kp.res != nullptr && ((kp.res_C | kp.res_coff) & 7) != 0)) return false;
+  if ((reinterpret_cast<uintptr_t>(kp.out) & 31) != 0) return false;  // 32-byte stores
+  if (kp.out_mode == PB_OUT_F16_NHWC || kp.out_mode == PB_OUT_F16_NHWC_UP2)
+    return ((kp.out_C | kp.out_coff) & 15) == 0 && (kp.cout_store & 15) == 0;
+  if (kp.out_mode == PB_OUT_F32_NHWC) return ((kp.out_C | kp.out_coff) & 7) == 0;  // 32-byte aligned 8-float groups
+  return false;
 }
 
 // SiLU on a pair with one reciprocal: 1/(1+ea) = db * r, 1/(1+eb) = da * r, r = 1/(da*db).  The exponent is clamped
 // to 2^60 so the product stays finite; silu(v) for v < -41 is below 1e-16 either way (fp16 zero).
+// Experimental (PADEL_B200_CONV_DEBUG bit 0): 1.5 instead of 2 MUFU operations per value, but measured within noise
+// on the YOLO programs (the epilogue is latency- not MUFU-bound), so the plain form stays the default.
 __device__ __forceinline__ void silu2(float& a, float& b) {
   const float ea = ex2_approx(fminf(a * -1.4426950408889634f, 60.f));
   const float eb = ex2_approx(fminf(b * -1.4426950408889634f, 60.f));
@@ -156,8 +163,16 @@ __device__ __forceinline__ void silu2(float& a, float& b) {
   b *= da * r;
 }
 
-__device__ __forceinline__ void epi_chunk(int act, bool has_res, uint32_t (&r)[16], const float* __restrict__ sbias,
-                                          __half* op, const uint4 (&rv)[2], bool valid) {
+// Where one thread's 16-channel chunk goes: byte pointer of the pixel (channel 0 of the N tile), byte strides of the
+// 2x2 replication (UP2 only) and the number of channels of this chunk that exist (fp32 heads may end mid-chunk).
+struct EpiOut {
+  int mode;       // PB_OUT_F16_NHWC | PB_OUT_F16_NHWC_UP2 | PB_OUT_F32_NHWC   (CTA-uniform)
+  size_t dx, dy;  // UP2: bytes to the pixel one to the right / one row down in the upsampled tensor
+};
+
+__device__ __forceinline__ void epi_chunk(int act, bool has_res, bool plain_silu, const EpiOut& eo, uint32_t (&r)[16],
+                                          const float* __restrict__ sbias, char* op, const uint4 (&rv)[2], bool valid,
+                                          int nvalid) {
   float v[16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -168,8 +183,13 @@ __device__ __forceinline__ void epi_chunk(int act, bool has_res, uint32_t (&r)[1
     v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
   }
   if (act == PB_ACT_SILU) {  // CTA-uniform
+    if (plain_silu) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) silu2(v[2 * i], v[2 * i + 1]);
+      for (int i = 0; i < 16; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) silu2(v[2 * i], v[2 * i + 1]);
+    }
   } else if (act == PB_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -189,23 +209,50 @@ __device__ __forceinline__ void epi_chunk(int act, bool has_res, uint32_t (&r)[1
       }
     }
   }
+  if (eo.mode == PB_OUT_F32_NHWC) {
+    if (!valid) return;
+    if (nvalid >= 16) {
+      uint4 w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        w[q] = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                          __float_as_uint(v[4 * q + 3]));
+      st_global_256(op, w[0], w[1]);
+      st_global_256(op + 32, w[2], w[3]);
+    } else {
+      float* o = reinterpret_cast<float*>(op);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) o[j] = v[j];
+    }
+    return;
+  }
   uint4 pk[2];
   __half2* h2 = reinterpret_cast<__half2*>(pk);
 #pragma unroll
   for (int j = 0; j < 8; ++j) h2[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-  if (valid) st_global_256(op, pk[0], pk[1]);
+  if (!valid) return;
+  st_global_256(op, pk[0], pk[1]);
+  if (eo.mode == PB_OUT_F16_NHWC_UP2) {
+    st_global_256(op + eo.dx, pk[0], pk[1]);
+    st_global_256(op + eo.dy, pk[0], pk[1]);
+    st_global_256(op + eo.dy + eo.dx, pk[0], pk[1]);
+  }
 }
 
 // One thread's share of a tile: `S` sub-tiles (accumulator sets `sub_cols` TMEM columns apart, pixels `sub_out` /
-// `sub_res` halves apart in the output / residual tensors), `nch` 16-column chunks each.  valid_mask bit j = the
-// thread's pixel of sub-tile j exists.  op0 / rp0 already point at channel 0 of this N tile.
-__device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, uint32_t t_addr0, int S, uint32_t sub_cols,
-                                              int nch, const float* __restrict__ sbias, __half* op0,
-                                              const __half* rp0, size_t sub_out, size_t sub_res,
+// `sub_res` BYTES / halves apart in the output / residual tensors), `nch` 16-column chunks each (`cout_n` channels of
+// this N tile exist).  valid_mask bit j = the thread's pixel of sub-tile j exists.  op0 / rp0 point at channel 0 of
+// this N tile.  Software pipeline: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed.
+__device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOut& eo, uint32_t t_addr0, int S,
+                                              uint32_t sub_cols, int nch, int cout_n, const float* __restrict__ sbias,
+                                              char* op0, const __half* rp0, size_t sub_out, size_t sub_res,
                                               uint32_t valid_mask) {
   uint32_t ra[16], rb[16];
   const int act = kp.act;
   const bool has_res = kp.res != nullptr;
+  const bool plain_silu = (kp.dbg_flags & 1) == 0;
+  const int cbytes = eo.mode == PB_OUT_F32_NHWC ? 64 : 32;  // bytes of one 16-channel chunk in the output
   int j = 0, c = 0;
   tmem_ld16(t_addr0, ra);
 #define PB_EPI_STAGE(cur, nxt)                                                                          \
@@ -225,7 +272,8 @@ __device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, uint32_t t_
     }                                                                                                   \
     tmem_ld_wait16(cur);                                                                                \
     if (more) tmem_ld16(t_addr0 + (uint32_t)jn * sub_cols + (uint32_t)(cn * 16), nxt);                  \
-    epi_chunk(act, has_res, cur, sbias + c * 16, op0 + (size_t)j * sub_out + c * 16, rv, valid);        \
+    epi_chunk(act, has_res, plain_silu, eo, cur, sbias + c * 16, op0 + (size_t)j * sub_out + (size_t)(c * cbytes), rv, valid, \
+              cout_n - c * 16);                                                                         \
     if (!more) break;                                                                                   \
     j = jn;                                                                                             \
     c = cn;                                                                                             \

@@ -75,7 +75,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int lane = threadIdx.x & 31;
   constexpr int S = kS;
   const int G = kp.hs_G;
-  const uint32_t row_bytes = (uint32_t)kp.KB * 2u;
+  const uint32_t row_bytes = (uint32_t)kp.KB * 2u;       // weight rows (and activation rows unless stride 2)
+  const uint32_t a_row_bytes = kp.hs_a_row_bytes;        // activation (halo) rows
   const int tap_groups = kp.hs_ntaps / G;
   // CTA-pair mode (cluster of 2, cta_group::2): both CTAs load their own halo and half of the weights, the even
   // CTA issues M=256 UMMAs over both, so every SM reads only half of B from its shared memory.
@@ -182,9 +183,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t tm_base = __shfl_sync(0xffffffffu, tmem_base, 0);
       int ast = 0, bst = 0, acc = 0;
       uint32_t aph = 0, bph = 0, acc_ph = 0;
-      const uint32_t sbo = (uint32_t)kp.hs_sbo_rows * row_bytes;
+      const uint32_t sbo = (uint32_t)kp.hs_sbo_rows * a_row_bytes;
       const uint32_t tap_b_units = ((uint32_t)(pair ? kp.BN / 2 : kp.BN) * row_bytes) >> 4;  // 16-byte units
-      const uint64_t sub_units = (uint64_t)((8u * row_bytes) >> 4);                            // next sub-tile: +8 pixels
+      const uint64_t sub_units = (uint64_t)((8u * a_row_bytes) >> 4);                          // next sub-tile: +8 pixels
       const uint32_t acc_cols = (uint32_t)kp.acc_cols;
       const uint32_t idesc = kp.idesc;
       int seq = -1;
@@ -204,7 +205,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (dbg) bwait += clock64() - ta;
           // Descriptor arithmetic is hoisted: per (channel block, weight stage) one base descriptor each; taps,
           // sub-tiles and k-steps only add precomputed 16-byte-unit offsets to the low word.
-          const uint64_t a_desc0 = umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), row_bytes, sbo);
+          const uint64_t a_desc0 = umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), a_row_bytes, sbo);
           for (int tg = 0; tg < tap_groups; ++tg) {
             const long long tb = dbg ? clock64() : 0;
             mbar_wait(&tail->b_full[bst], bph);
@@ -277,10 +278,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int j = 0; j < S; ++j) vm |= (uint32_t)((ow0 + 8 * j < kp.Wo) && (oh < kp.Ho)) << j;
         const size_t pix0 = ((size_t)t.n * kp.Ho + oh) * kp.Wo + ow0;
-        epilogue_fast(kp, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * kp.acc_cols), S,
-                               (uint32_t)kp.acc_cols, kp.cout_store >> 4, tail->bias,
-                               reinterpret_cast<__half*>(kp.out) + pix0 * kp.out_C + kp.out_coff,
-                               kp.res + pix0 * kp.res_C + kp.res_coff, (size_t)8 * kp.out_C, (size_t)8 * kp.res_C, vm);
+        EpiOut eo;
+        eo.mode = kp.out_mode;
+        const size_t esz = eo.mode == PB_OUT_F32_NHWC ? 4 : 2;
+        const size_t pxb = (size_t)kp.out_C * esz;  // bytes per output pixel
+        size_t opix = pix0, sub_out = 8 * pxb;
+        eo.dx = eo.dy = 0;
+        if (eo.mode == PB_OUT_F16_NHWC_UP2) {
+          opix = ((size_t)t.n * (2 * kp.Ho) + 2 * oh) * (2 * kp.Wo) + 2 * ow0;
+          eo.dx = pxb;
+          eo.dy = (size_t)(2 * kp.Wo) * pxb;
+          sub_out = 16 * pxb;
+        }
+        epilogue_fast(kp, eo, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * kp.acc_cols), S,
+                      (uint32_t)kp.acc_cols, (kp.cout_store + 15) >> 4, kp.cout_store, tail->bias,
+                      reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)kp.out_coff * esz,
+                      kp.res + pix0 * kp.res_C + kp.res_coff, sub_out, (size_t)8 * kp.res_C, vm);
       } else
       for (int j = 0; j < S; ++j) {
         EpiPix px;
@@ -404,6 +417,7 @@ int conv_stem_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.BN = BN;
   kp.n_ntiles = 1;
   kp.halo_bytes = 16u * 3u * (uint32_t)(8 * S) * 32u;
+  kp.hs_a_row_bytes = 32u;
   kp.a_bytes = (kp.halo_bytes + 1023u) & ~1023u;
   kp.b_tx_bytes = 3u * (uint32_t)BN * 32u;
   kp.b_bytes = (kp.b_tx_bytes + 1023u) & ~1023u;
@@ -502,6 +516,7 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.BN = BN;
   kp.n_ntiles = 1;
   kp.halo_bytes = 18u * (uint32_t)P * row_bytes;
+  kp.hs_a_row_bytes = row_bytes;
   kp.a_bytes = (kp.halo_bytes + 1023u) & ~1023u;
   kp.b_tx_bytes = (uint32_t)G * tap_bytes / (kp.pair ? 2u : 1u);  // per CTA
   kp.b_bytes = b_alloc;
@@ -555,6 +570,101 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PB_CHECK(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+  }
+  return 0;
+}
+
+// 3x3 / stride-2 conv over a whole C = 16 / 32 channel tensor.  The input is read through the pixel-pair view
+// (2C, W/2, 2, H/2, N) -- element (k, w2, ph, h2, n) = channel k % C of pixel (2*h2 + ph, 2*w2 + k / C) -- so one TMA
+// box (2C, 8S+1, 2, 17, 1) holds everything a 16 x 8S output tile needs, as rows of one PIXEL PAIR (4C bytes):
+//   smem row = ((h2i * 2 + ph) * P + w2i),  P = 8S + 1,  box origin (w2, h2) = (ow0 - 1, oh0 - 1).
+// Tap (r, s) of output (ohi, owi) reads input (2*oh + r - 1, 2*ow + s - 1):
+//   r = 0 -> (h2i, ph) = (ohi, 1)      r = 1 -> (ohi + 1, 0)      r = 2 -> (ohi + 1, 1)
+//   s = 0 -> (w2i, half) = (owi, 1)    s = 1 -> (owi + 1, 0)      s = 2 -> (owi + 1, 1)
+// i.e. again only a descriptor start offset (row offset * 4C + half * 2C bytes) with SBO = 2P rows, and K = C per tap
+// (the 32-byte k-step advance inside the swizzle row is the usual one).  Versus nine per-tap boxes of 2C-byte rows
+// this issues one TMA per tile with rows twice as long (TMA delivery of 32-byte rows is what bounds the per-tap path).
+int conv_halo_s2_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode) {
+  if (d->ksize != 3 || d->stride != 2 || d->cout_pad > 256 || d->c_in_off != 0 || d->C != d->cin ||
+      (d->cin != 16 && d->cin != 32))
+    return -1;
+  ConvKParams& kp = plan->kp;  // common fields already filled by the caller (KB = cin, kblocks = 1)
+  const int BN = d->cout_pad;
+  const uint32_t row_bytes = (uint32_t)d->cin * 2u;  // weight rows
+  const uint32_t a_row = 2u * row_bytes;             // pixel-pair rows
+  const int acc_cols = (BN + 31) / 32 * 32;
+  const uint32_t tap_bytes = (uint32_t)BN * row_bytes;
+  const uint32_t b_alloc = (9u * tap_bytes + 1023u) & ~1023u;  // all nine taps in one weight box
+  const size_t budget = 196 * 1024;
+  int S = 0;
+  for (int s = 4; s >= 1; s >>= 1) {
+    if (s * acc_cols * 2 > 512) continue;
+    const uint32_t halo = 34u * (uint32_t)(8 * s + 1) * a_row;
+    if ((size_t)2 * ((halo + 1023u) & ~1023u) + (size_t)2 * b_alloc <= budget) {
+      S = s;
+      break;
+    }
+  }
+  if (S == 0) return -1;
+  const int P = 8 * S + 1;
+  kp.pair = 0;
+  kp.KB = d->cin;
+  kp.kblocks = 1;
+  kp.hs_S = S;
+  kp.hs_P = P;
+  kp.hs_G = 9;
+  kp.hs_ntaps = 9;
+  kp.hs_sbo_rows = 2 * P;
+  kp.hs_x0 = -1;
+  kp.hs_y0 = -1;
+  kp.hs_a_row_bytes = a_row;
+  for (int r = 0; r < 3; ++r)
+    for (int q = 0; q < 3; ++q) {
+      const int row = ((r == 0 ? 0 : 1) * 2 + (r == 1 ? 0 : 1)) * P + (q == 0 ? 0 : 1);
+      const int half = q == 1 ? 0 : 1;
+      kp.hs_tap_off[r * 3 + q] = row;
+      kp.hs_tap_desc[r * 3 + q] = (int)(((uint32_t)row * a_row + (uint32_t)half * row_bytes) >> 4);
+    }
+  kp.BN = BN;
+  kp.n_ntiles = 1;
+  kp.halo_bytes = 34u * (uint32_t)P * a_row;
+  kp.a_bytes = (kp.halo_bytes + 1023u) & ~1023u;
+  kp.b_tx_bytes = 9u * tap_bytes;
+  kp.b_bytes = b_alloc;
+  kp.a_stages = 2;
+  kp.b_stages = 2;
+  kp.acc_cols = acc_cols;
+  kp.acc_stages = 512 / (S * acc_cols);
+  if (kp.acc_stages > kConvMaxAcc) kp.acc_stages = kConvMaxAcc;
+  kp.idesc = umma_idesc_f16(BN, 0);
+  kp.tiles_w = (kp.Wo + 8 * S - 1) / (8 * S);
+  kp.tiles_h = (kp.Ho + 15) / 16;
+  kp.tiles_n = kp.N;
+  kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
+  halo_finish_config(plan);
+  plan->variant = 1;
+  {
+    const cuuint64_t C = (cuuint64_t)d->C, W = (cuuint64_t)d->W, H = (cuuint64_t)d->H;
+    cuuint64_t dims[5] = {2 * C, W / 2, 2, H / 2, (cuuint64_t)d->N};
+    cuuint64_t strides[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)(2 * d->C), (cuuint32_t)P, 2, 17, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&plan->tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d->in), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        a_row == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "conv(halo s2): cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)d->cout_pad, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * d->cout_pad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)d->cin, (cuuint32_t)BN, 9};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&plan->tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d->weight), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "conv(halo s2): cuTensorMapEncodeTiled(W) failed with %d", (int)r);
   }
   return 0;
 }

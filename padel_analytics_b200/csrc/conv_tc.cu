@@ -219,12 +219,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // fused 1x1 head partial sums
       const float* sb = tail->bias + tc.nt * kp.BN;
       if (fast) {
-        int nch = kp.cout_store - tc.nt * kp.BN;
-        nch = (nch < kp.BN ? nch : kp.BN) >> 4;
-        if (nch > 0)
-          epilogue_fast(kp, t_addr, 1, 0u, nch, sb,
-                                 reinterpret_cast<__half*>(kp.out) + px.pix * kp.out_C + kp.out_coff + tc.nt * kp.BN,
-                                 kp.res + px.pix * kp.res_C + kp.res_coff + tc.nt * kp.BN, 0, 0, px.valid ? 1u : 0u);
+        int cn = kp.cout_store - tc.nt * kp.BN;  // channels of this N tile that exist
+        cn = cn < kp.BN ? cn : kp.BN;
+        if (cn > 0) {
+          EpiOut eo;
+          eo.mode = kp.out_mode;
+          const size_t esz = eo.mode == PB_OUT_F32_NHWC ? 4 : 2;
+          const size_t pxb = (size_t)kp.out_C * esz;
+          size_t opix = px.pix;
+          eo.dx = eo.dy = 0;
+          if (eo.mode == PB_OUT_F16_NHWC_UP2) {
+            opix = ((size_t)px.n * (2 * kp.Ho) + 2 * px.oh) * (2 * kp.Wo) + 2 * px.ow;
+            eo.dx = pxb;
+            eo.dy = (size_t)(2 * kp.Wo) * pxb;
+          }
+          epilogue_fast(kp, eo, t_addr, 1, 0u, (cn + 15) >> 4, cn, sb,
+                        reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)(kp.out_coff + tc.nt * kp.BN) * esz,
+                        kp.res + px.pix * kp.res_C + kp.res_coff + tc.nt * kp.BN, 0, 0, px.valid ? 1u : 0u);
+        }
       } else
       for (int c = 0; c < kp.BN; c += 32) {
         // two 16-column TMEM loads in flight, one wait
@@ -364,6 +376,10 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
   kp.head_n = d->head_n;
   kp.head_out = d->head_out;
   kp.dbg = g_conv_dbg;
+  {
+    const char* df = getenv("PADEL_B200_CONV_DEBUG");
+    kp.dbg_flags = df ? atoi(df) : 0;
+  }
   plan->variant = 0;
   if (stem) return conv_stem_setup(d, plan, encode);
   {
@@ -372,7 +388,7 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     const char* e = getenv("PADEL_B200_CONV_HALO");
     const int mode = e ? atoi(e) : 2;
     if (mode == 1 || (mode == 2 && d->cout_pad <= 192)) {
-      const int rc = conv_halo_setup(d, plan, encode);
+      const int rc = d->stride == 2 ? conv_halo_s2_setup(d, plan, encode) : conv_halo_setup(d, plan, encode);
       if (rc >= 0) return rc;
     }
   }

@@ -105,9 +105,11 @@ struct ConvKParams {
   float* head_out;
   int hs_S, hs_P, hs_G, a_stages, b_stages;  // halo variant: sub-tiles, halo pitch (px), taps per weight box, rings
   uint32_t halo_bytes;
+  uint32_t hs_a_row_bytes;  // bytes of one halo row in shared memory (KB*2; 2*KB*2 for the stride-2 pixel-pair rows)
   int hs_ntaps, hs_sbo_rows, hs_x0, hs_y0, hs_tile_h;  // taps served from the halo, 8-row group stride (rows), box origin offsets
   int hs_tap_off[9];                                   // smem row offset of each tap's first pixel
   int hs_tap_desc[9];                                  // the same in 16-byte descriptor units (offset * row_bytes / 16)
+  int dbg_flags;   // PADEL_B200_CONV_DEBUG: bit0 = paired-reciprocal SiLU, bit1 = no fast epilogue
   long long* dbg;  // optional timeline buffer (CTA 0, first 64 tiles): [role 0..2][64][4] clock64 stamps
 };
 
@@ -127,6 +129,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);  // -1: not applicable
 int conv_stem_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);
+int conv_halo_s2_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);  // -1: not applicable
 int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream);
 int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan);
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);

@@ -9,6 +9,7 @@ Network definition being replaced: /root/reference/trackers/ball_tracker/models.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -61,10 +62,14 @@ class TrackNetEngine:
                                    sd[f"{p}.bn.bias"].float(), sd[f"{p}.bn.running_mean"].float(),
                                    sd[f"{p}.bn.running_var"].float(), 1e-5)
                 self._w[p] = ops.pack_conv_weight(w, b, ops.pad16(ci) if ci != 27 else 32, cout, self.device)
-        # predictor 1x1 (64 -> 8) + sigmoid: a dedicated HBM-bound kernel (the fused-epilogue variant of the conv
-        # kernel exists but costs more: 512 FMAs per pixel on 8 epilogue warps stall the MMA pipeline)
+        # predictor 1x1 (64 -> 8) + sigmoid.  Default: a 1x1 tensor-core conv (fp16 weights, N = 16) writing the fp32
+        # NCHW planes -- HBM-bound at ~4.8 TB/s, 158 us per 32 frames.  PADEL_B200_TRACKNET_HEAD=pointwise selects the
+        # CUDA-core kernel with fp32 weights instead (308 us: ~800 instructions per 32 pixels, issue-bound).  The
+        # fused-epilogue variant of the conv kernel also exists but costs more (512 FMAs per pixel in the epilogue).
         self._head_w = sd["predictor.weight"].float().reshape(8, 64).contiguous().to(self.device)
         self._head_b = sd["predictor.bias"].float().contiguous().to(self.device)
+        self._w["predictor"] = ops.pack_conv_weight(sd["predictor.weight"].float().reshape(8, 64, 1, 1),
+                                                    sd["predictor.bias"].float(), 64, 16, self.device)
         self._build()
         return self
 
@@ -120,7 +125,10 @@ class TrackNetEngine:
         conv(self.cat3, 0, 192, "up_block_3.conv_1", self.u3a, 0)
         self._pred_new = self.pred[7:]
         conv(self.u3a, 0, 64, "up_block_3.conv_2", self.u3b, 0)
-        P.pointwise_head(self.u3b, self._head_w, self._head_b, self._pred_new)
+        if os.environ.get("PADEL_B200_TRACKNET_HEAD", "tc") == "tc":
+            conv(self.u3b, 0, 64, "predictor", self._pred_new, 0, L.OUT_F32_NCHW, SIG, k=1, store=8)
+        else:
+            P.pointwise_head(self.u3b, self._head_w, self._head_b, self._pred_new)
         self.prog = P
 
     # -- execution ---------------------------------------------------------------------------------------------

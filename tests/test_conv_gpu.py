@@ -114,6 +114,16 @@ HALO_CASES = [
     dict(N=1, H=36, W=64, cin=256, cout=256, k=3, s=1, act=L.ACT_RELU),          # S=1, two accumulator sets
     dict(N=2, H=16, W=32, cin=64, cout=27, k=3, s=1, act=L.ACT_NONE, out_mode=L.OUT_F32_NHWC, out_coff=64,
          out_extra=3),
+    # stride-2 halo (pixel-pair rows): 64-byte rows (cin 16) and 128-byte rows (cin 32), ragged tiles, slices
+    dict(N=2, H=40, W=56, cin=32, cout=64, k=3, s=2, act=L.ACT_SILU),
+    dict(N=3, H=34, W=18, cin=16, cout=16, k=3, s=2, act=L.ACT_SILU, out_coff=16, out_extra=16),
+    dict(N=1, H=96, W=160, cin=16, cout=32, k=3, s=2, act=L.ACT_RELU),
+    # fast epilogue, fp32 NHWC slice ending mid-chunk (39 = 2 x 16 + 7) at a 32-byte aligned offset
+    dict(N=2, H=16, W=32, cin=64, cout=39, k=1, s=1, act=L.ACT_NONE, out_mode=L.OUT_F32_NHWC, out_coff=64,
+         out_extra=25),
+    dict(N=2, H=24, W=40, cin=64, cout=39, k=3, s=1, act=L.ACT_SILU, out_mode=L.OUT_F32_NHWC, out_coff=8,
+         out_extra=1),
+    dict(N=2, H=20, W=24, cin=128, cout=256, k=1, s=1, act=L.ACT_RELU, out_mode=L.OUT_F16_NHWC_UP2, out_coff=32),
 ]
 
 
