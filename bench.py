@@ -362,7 +362,7 @@ def main():
 
     if rank == 0:
         h2d = B * H * W * 3  # one pinned-host -> device upload per batch, shared by the four trackers
-        d2h = sum(int(np.prod(st[k][2].shape)) * 4 for t in ("players", "pose", "court")
+        d2h = sum(int(np.prod(st[k]["host"][0][0].shape)) * 4 for t in ("players", "pose", "court")
                   for st in trackers[t].model._progs.values() for k in st if isinstance(k, tuple)) + (B + 7) * 16
         print(json.dumps({
             "metric": "frames/sec through trackers.runner (all 4 trackers)", "value": round(value, 2),

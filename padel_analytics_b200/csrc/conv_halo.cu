@@ -494,12 +494,19 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   const uint32_t b_alloc = ((uint32_t)G * tap_bytes + 1023u) & ~1023u;
   if (bestS == 0) return -1;
   const int S = bestS, P = 8 * S + 2;
-  // CTA-pair mode (cta_group::2): halves the weight bytes each SM reads per UMMA -- pays off on the operand-bound
-  // N = 64/128 layers with enough rows to pair up.  PADEL_B200_CONV_PAIR=0/1 overrides.
+  // CTA-pair mode (cta_group::2): one M=256 UMMA per instruction slot, each CTA of the pair fetching half of the
+  // weights.  Measured on TrackNet at batch 32 (profiles/r01_layers.txt): the deep-K narrow layers gain (192->64:
+  // 935 -> 757 us = 1.38 PFLOP/s, above the ~1.27 PFLOP/s a single CTA can issue at N = 64; 384->128: 768 -> 676 us;
+  // 128->128: 269 -> 231 us), shallow-K layers (cin <= 64) and the 2x2-replicating stores lose a few percent.
+  // Default rule: cin >= 128, plain fp16 store, enough tiles to fill the machine with pairs.
+  // PADEL_B200_CONV_PAIR=0/1 forces it off / on wherever it applies.
   {
     const char* ep = getenv("PADEL_B200_CONV_PAIR");
-    const int pm = ep ? atoi(ep) : 0;
-    kp.pair = (pm == 1 && BN % 32 == 0 && BN >= 32 && kp.Ho >= 32) ? 1 : 0;
+    const int pm = ep ? atoi(ep) : 2;
+    const bool can = BN % 32 == 0 && BN >= 32 && kp.Ho >= 32;
+    const long pair_tiles = (long)((d->W + 8 * S - 1) / (8 * S)) * ((kp.Ho + 31) / 32) * kp.N;
+    const bool want = d->cin >= 128 && d->out_mode == PB_OUT_F16_NHWC && pair_tiles >= 2L * (num_sms() / 2);
+    kp.pair = (can && (pm == 1 || (pm == 2 && want))) ? 1 : 0;
   }
   kp.hs_S = S;
   kp.hs_P = P;

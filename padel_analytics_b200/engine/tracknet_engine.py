@@ -173,7 +173,9 @@ class BallPipeline:
         self.mask = torch.zeros((B + 7, H, W), dtype=torch.uint8, device=self.dev)
         self.scratch = torch.zeros((B + 7, 5, H * W), dtype=torch.int32, device=self.dev)
         self.bbox = torch.zeros((B + 7, 4), dtype=torch.int32, device=self.dev)
-        self.bbox_host = torch.zeros((B + 7, 4), dtype=torch.int32).pin_memory()
+        self._host_ring = [torch.zeros((B + 7, 4), dtype=torch.int32).pin_memory() for _ in range(3)]
+        self._pending = [None] * 3
+        self._turn = 0
         self.ens = None
         # median: full-res RGB -> uint8 -> PIL resize (iterable.py:76-81), on device with the same kernel
         med = torch.as_tensor(median_rgb)
@@ -247,7 +249,12 @@ class BallPipeline:
                                              eng.W, 0.5, self.mask.data_ptr(), ens_ptr, L.stream_ptr()))
         L.check(L.lib().pb_ccl_bbox(self.mask.data_ptr(), nframes, eng.H, eng.W, self.scratch.data_ptr(),
                                     self.bbox.data_ptr(), L.stream_ptr()))
-        self.bbox_host[:nframes].copy_(self.bbox[:nframes], non_blocking=True)
+        slot = self._turn  # ring of pinned host copies: the caller may enqueue the next batch before collecting this one
+        self._turn = (slot + 1) % len(self._host_ring)
+        if self._pending[slot] is not None:
+            self._pending[slot]()  # an uncollected launch still owns this slot: resolve it first
+        host = self._host_ring[slot]
+        host[:nframes].copy_(self.bbox[:nframes], non_blocking=True)
         # carry the last 7 windows for the next batch (ball_tracker.py:523)
         carry = eng.pred[nb:nb + 7].clone()
         eng.pred[:7].copy_(carry)
@@ -255,10 +262,16 @@ class BallPipeline:
         done = torch.cuda.Event()
         done.record()
 
-        def finish():
-            done.synchronize()
-            return w0, self.bbox_host[:nframes].numpy().copy()
+        state = {"result": None}
 
+        def finish():
+            if state["result"] is None:
+                done.synchronize()
+                state["result"] = (w0, host[:nframes].numpy().copy())
+                self._pending[slot] = None
+            return state["result"]
+
+        self._pending[slot] = finish
         return finish
 
 

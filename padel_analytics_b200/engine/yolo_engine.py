@@ -208,10 +208,11 @@ class YoloEngine:
         c2f(cat20, 0, c3 + c4, 21, o5, 0, False)
 
         # heads: per level box / cls (/ kpt) branches -> one fp32 NHWC map (B,h,w,64+nc+nk)
-        # head map layout: [box 0:64 | kpt 64:64+nk | cls ...], 16-byte aligned slices so the epilogue stores float4
+        # head map layout: [box 0:64 | kpt 64:64+nk | cls ...], 32-byte aligned slices and rows so the epilogue's
+        # fast path stores 8 floats per instruction
         kpt_off = 64
-        cls_off = 64 + (self.nk + 3) // 4 * 4
-        fC = (cls_off + self.nc + 3) // 4 * 4
+        cls_off = 64 + (self.nk + 7) // 8 * 8
+        fC = (cls_off + self.nc + 7) // 8 * 8
         feats, levels = [], []
         branches = [("cv2", 64, 0), ("cv3", self.nc, cls_off)]
         if self.nk:
@@ -338,11 +339,20 @@ class YoloEngine:
                                    self.CAND_CAP, L.stream_ptr()))
         key = ("out", max_det)
         if key not in st:
-            st[key] = (torch.zeros((self.B, max_det, st["rowlen"]), dtype=torch.float32, device=self.device),
-                       torch.zeros((self.B,), dtype=torch.int32, device=self.device),
-                       torch.zeros((self.B, max_det, st["rowlen"]), dtype=torch.float32).pin_memory(),
-                       torch.zeros((2, self.B), dtype=torch.int32).pin_memory())
-        out, cnt, out_h, cnt_h = st[key]
+            # device results + a small ring of pinned host copies: a caller may enqueue the next batch before it
+            # has collected this one (FusedPass keeps one batch of look-ahead)
+            st[key] = dict(out=torch.zeros((self.B, max_det, st["rowlen"]), dtype=torch.float32, device=self.device),
+                           cnt=torch.zeros((self.B,), dtype=torch.int32, device=self.device),
+                           host=[(torch.zeros((self.B, max_det, st["rowlen"]), dtype=torch.float32).pin_memory(),
+                                  torch.zeros((2, self.B), dtype=torch.int32).pin_memory()) for _ in range(3)],
+                           pending=[None] * 3, turn=0)
+        ring = st[key]
+        out, cnt = ring["out"], ring["cnt"]
+        slot = ring["turn"]
+        ring["turn"] = (slot + 1) % 3
+        if ring["pending"][slot] is not None:  # an uncollected launch still owns this slot: resolve it first
+            self._detect_resolve(ring["pending"][slot])
+        out_h, cnt_h = ring["host"][slot]
         L.check(lib.pb_yolo_nms(st["cand"].data_ptr(), st["cand_anchor"].data_ptr(), st["cand_count"].data_ptr(),
                                 self.B, self.CAND_CAP, st["rowlen"], float(iou), max_det, out.data_ptr(),
                                 cnt.data_ptr(), L.stream_ptr()))
@@ -351,14 +361,22 @@ class YoloEngine:
         cnt_h[1].copy_(st["cand_count"], non_blocking=True)
         done = torch.cuda.Event()
         done.record()
-        return (done, out_h, cnt_h, n)
+        handle = dict(done=done, out_h=out_h, cnt_h=cnt_h, n=n, ring=ring, slot=slot, result=None)
+        ring["pending"][slot] = handle
+        return handle
+
+    def _detect_resolve(self, handle):
+        if handle["result"] is None:
+            handle["done"].synchronize()
+            n, cnt_h = handle["n"], handle["cnt_h"]
+            if int(cnt_h[1][:n].max()) > self.CAND_CAP:
+                raise L.PbError(f"YoloEngine: {int(cnt_h[1][:n].max())} candidates exceed CAND_CAP={self.CAND_CAP}")
+            handle["result"] = (handle["out_h"].numpy().copy(), cnt_h[0].numpy().copy())
+            handle["ring"]["pending"][handle["slot"]] = None
+        return handle["result"]
 
     def _detect_finish(self, handle):
-        done, out_h, cnt_h, n = handle
-        done.synchronize()
-        if int(cnt_h[1][:n].max()) > self.CAND_CAP:
-            raise L.PbError(f"YoloEngine: {int(cnt_h[1][:n].max())} candidates exceed CAND_CAP={self.CAND_CAP}")
-        return out_h.numpy(), cnt_h[0].numpy()
+        return self._detect_resolve(handle)
 
     def _results(self, rows, counts, n, net_hw, orig_hw):
         """scale_boxes / scale_coords / clip / keypoint conf<0.5 -> 0 (ultralytics ops, SURVEY App. A.4 vi-vii),

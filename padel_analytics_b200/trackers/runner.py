@@ -55,6 +55,7 @@ class FusedPass:
         self.staging = [torch.empty((batch_size,) + self.hw + (3,), dtype=torch.uint8, device=self.dev)
                         for _ in range(2)]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [None, None]  # per staging slot: event after the device work that read it
         for t in trackers.values():
             if isinstance(t, BallTracker):
                 t.stream_begin(self.hw, total_frames, first_frame, emit_range)
@@ -66,11 +67,17 @@ class FusedPass:
         if frames.device.type == "cuda":
             return frames
         with torch.cuda.stream(self.copy_stream):
+            if self.consumed[slot] is not None:  # the batch that last used this slot must have been read
+                self.copy_stream.wait_event(self.consumed[slot])
             self.staging[slot][:n].copy_(frames, non_blocking=True)
             self.ready[slot].record(self.copy_stream)
         return self.staging[slot][:n]
 
     def _process(self, fr: torch.Tensor) -> dict:
+        return self._finish(self._launch(fr))
+
+    def _launch(self, fr: torch.Tensor):
+        """Enqueue the device work of every tracker for this batch (no host synchronisation)."""
         pending = []
         main = torch.cuda.current_stream()
         forked = []
@@ -98,12 +105,17 @@ class FusedPass:
         for s in forked:  # the caller's stream (and the next upload into this staging slot) follows all of them
             main.wait_stream(s)
         pending.sort(key=lambda p: list(self.trackers).index(p[0]))
+        return pending, fr.shape[0]
+
+    def _finish(self, launched) -> dict:
+        """Wait for each tracker's results in turn and run its host post-processing."""
+        pending, nfr = launched
         out = {}
         for name, t, fin in pending:  # ... then finish in the same order
             if isinstance(t, BallTracker):
                 out[name] = fin()
             elif fin is None:
-                out[name] = [t.fixed_keypoints_detection] * fr.shape[0]
+                out[name] = [t.fixed_keypoints_detection] * nfr
             elif isinstance(t, PlayerTracker):
                 out[name] = t.postprocess(fin())
             else:
@@ -114,19 +126,32 @@ class FusedPass:
         """batches: iterable of uint8 (n,H,W,3) BGR batches (pinned host tensors, device tensors or lists of frames),
         n <= batch_size.  Yields one {tracker name: results} dict per batch."""
         it = iter(batches)
+        main = torch.cuda.current_stream()
+
+        def start(frames, i):
+            """upload (copy stream) + enqueue all device work of batch i; returns the launch record"""
+            dev = self._upload(frames, i % 2)
+            staged = dev.data_ptr() == self.staging[i % 2].data_ptr()
+            if staged:
+                main.wait_event(self.ready[i % 2])
+            rec = self._launch(dev)
+            if staged:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self.consumed[i % 2] = ev
+            return rec
+
         cur = next(it, None)
         if cur is None:
             return
-        cur_dev = self._upload(cur, 0)
-        i = 0
-        while cur is not None:
+        rec, i = start(cur, 0), 0
+        while rec is not None:
+            # one batch of look-ahead: batch i+1 is uploaded and fully enqueued before batch i's results are collected,
+            # so the device never waits for the host post-processing (ByteTrack, result objects) of the batch before
             nxt = next(it, None)
-            nxt_dev = self._upload(nxt, (i + 1) % 2) if nxt is not None else None  # overlaps with the compute below
-            if cur_dev.data_ptr() == self.staging[i % 2].data_ptr():
-                torch.cuda.current_stream().wait_event(self.ready[i % 2])
-            yield self._process(cur_dev)
-            cur, cur_dev = nxt, nxt_dev
-            i += 1
+            nrec = start(nxt, i + 1) if nxt is not None else None
+            yield self._finish(rec)
+            rec, i = nrec, i + 1
 
 
 class TrackingRunner:
