@@ -170,10 +170,9 @@ struct EpiOut {
   size_t dx, dy;  // UP2: bytes to the pixel one to the right / one row down in the upsampled tensor
 };
 
-__device__ __forceinline__ void epi_chunk(int act, bool has_res, bool plain_silu, const EpiOut& eo, uint32_t (&r)[16],
-                                          const float* __restrict__ sbias, char* op, const uint4 (&rv)[2], bool valid,
-                                          int nvalid) {
-  float v[16];
+// bias + activation (+ residual) of one 16-column chunk of this thread's pixel
+__device__ __forceinline__ void epi_compute16(int act, bool has_res, bool plain_silu, uint32_t (&r)[16],
+                                              const float* __restrict__ sbias, const uint4 (&rv)[2], float (&v)[16]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * q);
@@ -209,6 +208,13 @@ __device__ __forceinline__ void epi_chunk(int act, bool has_res, bool plain_silu
       }
     }
   }
+}
+
+__device__ __forceinline__ void epi_chunk(int act, bool has_res, bool plain_silu, const EpiOut& eo, uint32_t (&r)[16],
+                                          const float* __restrict__ sbias, char* op, const uint4 (&rv)[2], bool valid,
+                                          int nvalid) {
+  float v[16];
+  epi_compute16(act, has_res, plain_silu, r, sbias, rv, v);
   if (eo.mode == PB_OUT_F32_NHWC) {
     if (!valid) return;
     if (nvalid >= 16) {
@@ -283,6 +289,102 @@ __device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOu
     PB_EPI_STAGE(rb, ra)
   }
 #undef PB_EPI_STAGE
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Staged variant of the fast epilogue (fp16 NHWC / UP2 stores, >= 2 chunks per pixel).
+// Measured with scripts/exp_epi_bench.py: a warp store whose 32 lanes each write 32 bytes of a DIFFERENT 128-byte
+// line (lane = pixel, pixel stride = out_C * 2 bytes) costs ~64 cycles of a per-SM serial resource (~2 cycles per line
+// touched), i.e. 16 B/clk/SM no matter how many warps store -- the limiter of every small-channel layer.  Here each
+// warp transposes groups of up to four chunks (64 channels = one 128-byte line per pixel) through a private 4 KB
+// shared-memory tile (XOR-swizzled, conflict-free both ways) so that four lanes write the four 32-byte pieces of ONE
+// pixel: a store instruction then touches 8 lines instead of 32.
+// RESULT: slower on every layer tried (1x1 32->32 @320^2: 141 -> 399 us; 3x3 64->192 @160^2: 191 -> 241 us), so the
+// limit is not the number of lines per instruction -- more likely bytes moved from registers (16 B/clk/SM).  Kept
+// behind PADEL_B200_CONV_DEBUG bit 2 as a documented negative result; the product path uses epilogue_fast.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t epi_swz(int row) { return (uint32_t)(((row & 3) << 1) | ((row >> 2) & 1)); }
+
+__device__ __forceinline__ void epilogue_fast_staged(const ConvKParams& kp, const EpiOut& eo, uint32_t t_addr0, int S,
+                                                     uint32_t sub_cols, int nch, const float* __restrict__ sbias,
+                                                     char* op0, const __half* rp0, size_t sub_out, size_t sub_res,
+                                                     uint32_t valid_mask, char* stage, size_t px_step) {
+  uint32_t ra[16], rb[16];
+  const int act = kp.act;
+  const bool has_res = kp.res != nullptr;
+  const bool plain_silu = (kp.dbg_flags & 1) == 0;
+  const int lane = threadIdx.x & 31, jj = lane & 3, g4 = lane & ~3;
+  char* wrow = stage + lane * 128;
+  const uint32_t wsw = epi_swz(lane);
+  tmem_ld16(t_addr0, ra);
+  for (int j = 0; j < S; ++j) {
+    const bool valid = ((valid_mask >> j) & 1u) != 0;
+    const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+    char* opj = op0 + (size_t)j * sub_out;
+    const __half* rpj = rp0 + (size_t)j * sub_res;
+    const uint32_t t_j = t_addr0 + (uint32_t)j * sub_cols;
+    for (int c0 = 0; c0 < nch; c0 += 4) {
+      const int gsz = nch - c0 < 4 ? nch - c0 : 4;
+      int jn = j, cn0 = c0 + 4;
+      if (cn0 >= nch) {
+        cn0 = 0;
+        ++jn;
+      }
+      const bool more_groups = jn < S;
+      const uint32_t t_next = t_addr0 + (uint32_t)jn * sub_cols + (uint32_t)(cn0 * 16);
+#define PB_EPI_GSTAGE(s, cur, nxt)                                                                       \
+  if (s < gsz) {                                                                                         \
+    const int c = c0 + s;                                                                                \
+    uint4 rv[2] = {};                                                                                    \
+    if (has_res && valid) {                                                                              \
+      const uint4* rp = reinterpret_cast<const uint4*>(rpj + c * 16);                                    \
+      rv[0] = __ldg(rp);                                                                                 \
+      rv[1] = __ldg(rp + 1);                                                                             \
+    }                                                                                                    \
+    tmem_ld_wait16(cur);                                                                                 \
+    bool deferred = false;                                                                               \
+    if (s + 1 < gsz) tmem_ld16(t_j + (uint32_t)((c + 1) * 16), nxt);                                     \
+    else if (more_groups) {                                                                              \
+      if ((s & 1) == 1) tmem_ld16(t_next, nxt); /* nxt == ra: the next group's first buffer */           \
+      else deferred = true;                     /* cur == ra: reload it once this chunk is consumed */    \
+    }                                                                                                    \
+    float v[16];                                                                                         \
+    epi_compute16(act, has_res, plain_silu, cur, sbias + c * 16, rv, v);                                 \
+    if (deferred) tmem_ld16(t_next, cur);                                                                \
+    uint4 pk[2];                                                                                         \
+    __half2* h2 = reinterpret_cast<__half2*>(pk);                                                        \
+    _Pragma("unroll") for (int q = 0; q < 8; ++q) h2[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);    \
+    *reinterpret_cast<uint4*>(wrow + (((uint32_t)(2 * s) ^ wsw) << 4)) = pk[0];                          \
+    *reinterpret_cast<uint4*>(wrow + (((uint32_t)(2 * s + 1) ^ wsw) << 4)) = pk[1];                      \
+  }
+      PB_EPI_GSTAGE(0, ra, rb)
+      PB_EPI_GSTAGE(1, rb, ra)
+      PB_EPI_GSTAGE(2, ra, rb)
+      PB_EPI_GSTAGE(3, rb, ra)
+#undef PB_EPI_GSTAGE
+      __syncwarp();
+      if (jj < gsz) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = g4 + k;
+          const uint32_t rsw = epi_swz(r);
+          const char* rrow = stage + r * 128;
+          const uint4 a = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)(2 * jj) ^ rsw) << 4));
+          const uint4 b = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)(2 * jj + 1) ^ rsw) << 4));
+          if ((vm >> r) & 1u) {
+            char* o = opj + (ptrdiff_t)(k - jj) * (ptrdiff_t)px_step + (size_t)((c0 + jj) * 32);
+            st_global_256(o, a, b);
+            if (eo.mode == PB_OUT_F16_NHWC_UP2) {
+              st_global_256(o + eo.dx, a, b);
+              st_global_256(o + eo.dy, a, b);
+              st_global_256(o + eo.dy + eo.dx, a, b);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
 }
 
 }  // namespace pb

@@ -290,10 +290,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           eo.dy = (size_t)(2 * kp.Wo) * pxb;
           sub_out = 16 * pxb;
         }
-        epilogue_fast(kp, eo, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * kp.acc_cols), S,
-                      (uint32_t)kp.acc_cols, (kp.cout_store + 15) >> 4, kp.cout_store, tail->bias,
-                      reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)kp.out_coff * esz,
-                      kp.res + pix0 * kp.res_C + kp.res_coff, sub_out, (size_t)8 * kp.res_C, vm);
+        const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * kp.acc_cols);
+        char* obase = reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)kp.out_coff * esz;
+        if (kp.epi_stage_off != 0 && eo.mode != PB_OUT_F32_NHWC && kp.cout_store >= 32)
+          epilogue_fast_staged(kp, eo, t0, S, (uint32_t)kp.acc_cols, kp.cout_store >> 4, tail->bias, obase,
+                               kp.res + pix0 * kp.res_C + kp.res_coff, sub_out, (size_t)8 * kp.res_C, vm,
+                               reinterpret_cast<char*>(smem) + kp.epi_stage_off + (egroup * 4 + quarter) * 4096,
+                               eo.mode == PB_OUT_F16_NHWC_UP2 ? 2 * pxb : pxb);
+        else
+          epilogue_fast(kp, eo, t0, S, (uint32_t)kp.acc_cols, (kp.cout_store + 15) >> 4, kp.cout_store, tail->bias,
+                        obase, kp.res + pix0 * kp.res_C + kp.res_coff, sub_out, (size_t)8 * kp.res_C, vm);
       } else
       for (int j = 0; j < S; ++j) {
         EpiPix px;
@@ -370,6 +376,7 @@ static void halo_finish_config(ConvPlan* plan) {
   const bool occ2 = !kp.pair && (!eo || atoi(eo) != 0) && need <= 110 * 1024 && set_cols * 2 <= 256 &&
                     kp.total_tiles > num_sms();
   plan->smem_bytes = need;
+  kp.epi_stage_off = 0;
   if (occ2) {
     if (kp.acc_stages * set_cols > 256) kp.acc_stages = 256 / set_cols;
     kp.tmem_cols = 256;
@@ -385,6 +392,18 @@ static void halo_finish_config(ConvPlan* plan) {
     if (kp.pair) {  // total_tiles counts pair tiles: two CTAs each
       const int pairs = kp.total_tiles < num_sms() / 2 ? kp.total_tiles : num_sms() / 2;
       plan->grid = 2 * pairs;
+    }
+  }
+  // store staging (epilogue_fast_staged): 4 KB per epilogue warp behind the tail, when it fits
+  {
+    const bool f16 = kp.out_mode == PB_OUT_F16_NHWC || kp.out_mode == PB_OUT_F16_NHWC_UP2;
+    const size_t tail_end = ((size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes +
+                             sizeof(HaloSmemTail) + 127) & ~(size_t)127;
+    const size_t stage_bytes = (size_t)kp.egroups * 4 * 4096;
+    const size_t limit = occ2 ? 112 * 1024 : 227 * 1024;
+    if (f16 && kp.cout_store >= 32 && !kp.pair && (kp.dbg_flags & 4) != 0 && tail_end + stage_bytes + 1024 <= limit) {
+      kp.epi_stage_off = (uint32_t)tail_end;
+      if (plan->smem_bytes < tail_end + stage_bytes + 1024) plan->smem_bytes = tail_end + stage_bytes + 1024;
     }
   }
 }

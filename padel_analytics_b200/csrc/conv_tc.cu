@@ -233,9 +233,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             eo.dx = pxb;
             eo.dy = (size_t)(2 * kp.Wo) * pxb;
           }
-          epilogue_fast(kp, eo, t_addr, 1, 0u, (cn + 15) >> 4, cn, sb,
-                        reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)(kp.out_coff + tc.nt * kp.BN) * esz,
-                        kp.res + px.pix * kp.res_C + kp.res_coff + tc.nt * kp.BN, 0, 0, px.valid ? 1u : 0u);
+          char* obase = reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)(kp.out_coff + tc.nt * kp.BN) * esz;
+          const __half* rbase = kp.res + px.pix * kp.res_C + kp.res_coff + tc.nt * kp.BN;
+          if (kp.epi_stage_off != 0 && eo.mode != PB_OUT_F32_NHWC && cn >= 32 && (cn & 15) == 0)
+            epilogue_fast_staged(kp, eo, t_addr, 1, 0u, cn >> 4, sb, obase, rbase, 0, 0, px.valid ? 1u : 0u,
+                                 reinterpret_cast<char*>(smem) + kp.epi_stage_off + (egroup * 4 + quarter) * 4096,
+                                 eo.mode == PB_OUT_F16_NHWC_UP2 ? 2 * pxb : pxb);
+          else
+            epilogue_fast(kp, eo, t_addr, 1, 0u, (cn + 15) >> 4, cn, sb, obase, rbase, 0, 0, px.valid ? 1u : 0u);
         }
       } else
       for (int c = 0; c < kp.BN; c += 32) {
@@ -472,6 +477,18 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     kp.egroups = conv_pick_egroups(kp.acc_stages);
     plan->threads = conv_threads_for(kp.egroups);
     plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+  }
+  // store staging (epilogue_fast_staged): 4 KB per epilogue warp behind the tail, when it fits
+  kp.epi_stage_off = 0;
+  {
+    const bool f16 = d->out_mode == PB_OUT_F16_NHWC || d->out_mode == PB_OUT_F16_NHWC_UP2;
+    const size_t tail_end = ((size_t)stages * stage_bytes + sizeof(ConvSmemTail) + 127) & ~(size_t)127;
+    const size_t stg = (size_t)kp.egroups * 4 * 4096;
+    const size_t limit = occ2 ? 112 * 1024 : 227 * 1024;
+    if (f16 && kp.BN >= 32 && (kp.dbg_flags & 4) != 0 && tail_end + stg + 1024 <= limit) {
+      kp.epi_stage_off = (uint32_t)tail_end;
+      if (plan->smem_bytes < tail_end + stg + 1024) plan->smem_bytes = tail_end + stg + 1024;
+    }
   }
 
   const CUtensorMapSwizzle swz = kp.KB == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
