@@ -301,8 +301,10 @@ __device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOu
 // pixel: a store instruction then touches 8 lines instead of 32.
 // RESULT: slower on every layer tried (1x1 32->32 @320^2: 141 -> 399 us; 3x3 64->192 @160^2: 191 -> 241 us), so the
 // limit is not the number of lines per instruction -- more likely bytes moved from registers (16 B/clk/SM).  Kept
-// behind PADEL_B200_CONV_DEBUG bit 2 as a documented negative result; the product path uses epilogue_fast.
+// behind -DPB_EXPERIMENTAL_STAGED_EPILOGUE + PADEL_B200_CONV_DEBUG bit 2 as a documented negative result; the
+// product path uses epilogue_fast.
 // ------------------------------------------------------------------------------------------------------------
+#ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE  // compiling it in costs registers / spills in the product kernels: off
 __device__ __forceinline__ uint32_t epi_swz(int row) { return (uint32_t)(((row & 3) << 1) | ((row >> 2) & 1)); }
 
 __device__ __forceinline__ void epilogue_fast_staged(const ConvKParams& kp, const EpiOut& eo, uint32_t t_addr0, int S,
@@ -386,5 +388,6 @@ __device__ __forceinline__ void epilogue_fast_staged(const ConvKParams& kp, cons
     }
   }
 }
+#endif  // PB_EXPERIMENTAL_STAGED_EPILOGUE
 
 }  // namespace pb

@@ -292,12 +292,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * kp.acc_cols);
         char* obase = reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)kp.out_coff * esz;
+#ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE
         if (kp.epi_stage_off != 0 && eo.mode != PB_OUT_F32_NHWC && kp.cout_store >= 32)
           epilogue_fast_staged(kp, eo, t0, S, (uint32_t)kp.acc_cols, kp.cout_store >> 4, tail->bias, obase,
                                kp.res + pix0 * kp.res_C + kp.res_coff, sub_out, (size_t)8 * kp.res_C, vm,
                                reinterpret_cast<char*>(smem) + kp.epi_stage_off + (egroup * 4 + quarter) * 4096,
                                eo.mode == PB_OUT_F16_NHWC_UP2 ? 2 * pxb : pxb);
         else
+#endif
           epilogue_fast(kp, eo, t0, S, (uint32_t)kp.acc_cols, (kp.cout_store + 15) >> 4, kp.cout_store, tail->bias,
                         obase, kp.res + pix0 * kp.res_C + kp.res_coff, sub_out, (size_t)8 * kp.res_C, vm);
       } else
@@ -401,7 +403,7 @@ static void halo_finish_config(ConvPlan* plan) {
                              sizeof(HaloSmemTail) + 127) & ~(size_t)127;
     const size_t stage_bytes = (size_t)kp.egroups * 4 * 4096;
     const size_t limit = occ2 ? 112 * 1024 : 227 * 1024;
-    if (f16 && kp.cout_store >= 32 && !kp.pair && (kp.dbg_flags & 4) != 0 && tail_end + stage_bytes + 1024 <= limit) {
+    if (f16 && kp.cout_store >= 32 && !kp.pair && (kp.dbg_flags & 4) != 0 && tail_end + stage_bytes + 1024 <= limit && kStagedEpilogueBuilt) {
       kp.epi_stage_off = (uint32_t)tail_end;
       if (plan->smem_bytes < tail_end + stage_bytes + 1024) plan->smem_bytes = tail_end + stage_bytes + 1024;
     }

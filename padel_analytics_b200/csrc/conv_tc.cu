@@ -235,11 +235,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           char* obase = reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)(kp.out_coff + tc.nt * kp.BN) * esz;
           const __half* rbase = kp.res + px.pix * kp.res_C + kp.res_coff + tc.nt * kp.BN;
+#ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE
           if (kp.epi_stage_off != 0 && eo.mode != PB_OUT_F32_NHWC && cn >= 32 && (cn & 15) == 0)
             epilogue_fast_staged(kp, eo, t_addr, 1, 0u, cn >> 4, sb, obase, rbase, 0, 0, px.valid ? 1u : 0u,
                                  reinterpret_cast<char*>(smem) + kp.epi_stage_off + (egroup * 4 + quarter) * 4096,
                                  eo.mode == PB_OUT_F16_NHWC_UP2 ? 2 * pxb : pxb);
           else
+#endif
             epilogue_fast(kp, eo, t_addr, 1, 0u, (cn + 15) >> 4, cn, sb, obase, rbase, 0, 0, px.valid ? 1u : 0u);
         }
       } else
@@ -485,7 +487,7 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     const size_t tail_end = ((size_t)stages * stage_bytes + sizeof(ConvSmemTail) + 127) & ~(size_t)127;
     const size_t stg = (size_t)kp.egroups * 4 * 4096;
     const size_t limit = occ2 ? 112 * 1024 : 227 * 1024;
-    if (f16 && kp.BN >= 32 && (kp.dbg_flags & 4) != 0 && tail_end + stg + 1024 <= limit) {
+    if (f16 && kp.BN >= 32 && (kp.dbg_flags & 4) != 0 && tail_end + stg + 1024 <= limit && kStagedEpilogueBuilt) {
       kp.epi_stage_off = (uint32_t)tail_end;
       if (plan->smem_bytes < tail_end + stg + 1024) plan->smem_bytes = tail_end + stg + 1024;
     }

@@ -55,6 +55,11 @@ inline int conv_pick_egroups(int acc_stages) {
   return want < 1 ? 1 : want;
 }
 constexpr int kConvMaxCout = 1024;
+#ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE
+constexpr bool kStagedEpilogueBuilt = true;
+#else
+constexpr bool kStagedEpilogueBuilt = false;
+#endif
 
 // Division by a launch-time constant as multiply-high + shift (dividend < 2^31): the per-tile coordinate decode of the
 // persistent kernels would otherwise spend ~25 instructions per runtime `/` or `%` in every warp, every tile.
