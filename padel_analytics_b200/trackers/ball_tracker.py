@@ -298,13 +298,17 @@ class BallTracker(Tracker):
             res[n] = (cx, cy, 0 if (cx == 0 and cy == 0) else 1)
         return res
 
+    def inpaint_xyv(self, xyv: dict, total_frames: int) -> dict:
+        """Apply the InpaintNet stage to a complete {frame: (x, y, vis)} trajectory (no-op without an inpainting model
+        or when frames are missing); used by predict_frames and by the sharded runner on rank 0."""
+        if getattr(self, "inpaintnet", None) is None or len(xyv) != total_frames:
+            return xyv
+        # the reference feeds every TrackNet prediction (frames 0..T-1) to the inpainting stage
+        order = sorted(xyv)
+        return self._inpaint_stage([xyv[n][0] for n in order], [xyv[n][1] for n in order], [xyv[n][2] for n in order])
+
     def predict_frames(self, frame_generator: Iterable[np.ndarray], total_frames: int, **kwargs) -> list[Ball]:
-        xyv = self.track_xyv(frame_generator, total_frames)
-        if self.inpaintnet is not None and len(xyv) == total_frames:
-            # the reference feeds every TrackNet prediction (frames 0..T-1) to the inpainting stage
-            order = sorted(xyv)
-            xyv = self._inpaint_stage([xyv[n][0] for n in order], [xyv[n][1] for n in order],
-                                      [xyv[n][2] for n in order])
+        xyv = self.inpaint_xyv(self.track_xyv(frame_generator, total_frames), total_frames)
         balls = []
         for n in range(total_frames):  # ball_tracker.py:675-698 (missing frames -> (0,0), visibility 0)
             if n in xyv:

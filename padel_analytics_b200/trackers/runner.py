@@ -231,6 +231,7 @@ class TrackingRunner:
             xyv = {}
             for p in parts:
                 xyv.update(p)
+            xyv = tracker.inpaint_xyv(xyv, total)  # whole-trajectory stage: after the shards are merged
             tracker.results.predictions = [
                 Ball(frame=n, xy=(xyv[n][0], xyv[n][1]), visibility=xyv[n][2]) if n in xyv
                 else Ball(frame=n, xy=(0.0, 0.0), visibility=0) for n in range(total)]

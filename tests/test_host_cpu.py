@@ -1,5 +1,6 @@
 """CPU: C-ABI surface, host-side tracker logic, sharding maths and the world-size-2 gloo path."""
 import json
+import math
 import os
 import re
 import subprocess
@@ -168,3 +169,75 @@ dist.destroy_process_group()
                         "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)], capture_output=True,
                        text=True, env=env, timeout=240)
     assert "WORLD2_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_ball_tracker_inpaint_host_logic_reproduces_reference_golden():
+    """BallTracker._inpaint_stage (product host code: mask, sequences, blend, COOR_TH, coordinate ensemble, float32 pixel
+    conversion) driven with the CPU oracle network instead of the CUDA kernel must reproduce the golden produced by the
+    reference BallTracker's own inpainting branch exactly (tests/golden/inpaint_ref.npz)."""
+    from pathlib import Path
+    import torch
+    from oracle import inpaint as OI
+    from padel_analytics_b200.trackers import sv_compat as sv
+    from padel_analytics_b200.trackers.ball_tracker import BallTracker
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "inpaint_ref.npz")
+    net = OI.load_inpaintnet(OI.make_inpaintnet())
+    bt = object.__new__(BallTracker)  # no CUDA here: skip the engine construction, set what the stage reads
+    bt.inpaintnet_seq_len = int(g["seq_len"])
+    bt.DELTA_T = 1 / math.sqrt(bt.HEIGHT ** 2 + bt.WIDTH ** 2)  # what __init__ sets (ball_tracker.py:246-247)
+    bt.COOR_TH = bt.DELTA_T * 50
+    bt.video_info = sv.VideoInfo(width=int(g["W"]), height=int(g["H"]), fps=30.0, total_frames=int(g["T"]))
+
+    def cpu_net(coor, mask):
+        with torch.no_grad():
+            return net(coor, mask)
+
+    bt.inpaintnet = cpu_net
+    res = bt._inpaint_stage(g["x"].tolist(), g["y"].tolist(), g["vis"].tolist())
+    n = len(g["X"])
+    assert [res[i][0] for i in range(n)] == g["X"].tolist()
+    assert [res[i][1] for i in range(n)] == g["Y"].tolist()
+    assert [res[i][2] for i in range(n)] == g["V"].tolist()
+    # and the mask generator agrees with the oracle's on random trajectories
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        T = int(rng.integers(5, 80))
+        vis = (rng.random(T) > 0.4).astype(int)
+        y = rng.integers(0, 1080, T) * vis
+        a = BallTracker._generate_inpaint_mask(y.tolist(), vis.tolist(), th_h=54.0)
+        b = OI.generate_inpaint_mask(y.tolist(), vis.tolist(), th_h=54.0)
+        assert list(a) == list(b)
+
+
+def test_runner_assemble_applies_inpainting_after_merging_shards():
+    """TrackingRunner._assemble: the ball shards are merged first, then the whole-trajectory InpaintNet stage runs once
+    (same result as the unsharded BallTracker.predict_frames path, checked against the reference golden)."""
+    from pathlib import Path
+    import torch
+    from oracle import inpaint as OI
+    from padel_analytics_b200.trackers import sv_compat as sv
+    from padel_analytics_b200.trackers.ball_tracker import BallTracker
+    from padel_analytics_b200.trackers.runner import TrackingRunner
+    from padel_analytics_b200.trackers.tracker import TrackingResults
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "inpaint_ref.npz")
+    net = OI.load_inpaintnet(OI.make_inpaintnet())
+    bt = object.__new__(BallTracker)
+    bt.results = TrackingResults()
+    bt.inpaintnet_seq_len = int(g["seq_len"])
+    bt.DELTA_T = 1 / math.sqrt(bt.HEIGHT ** 2 + bt.WIDTH ** 2)
+    bt.COOR_TH = bt.DELTA_T * 50
+    bt.video_info = sv.VideoInfo(width=int(g["W"]), height=int(g["H"]), fps=30.0, total_frames=int(g["T"]))
+    bt.inpaintnet = lambda c, m: net(c, m).detach()
+    T = len(g["x"])
+    xyv = {n: (int(g["x"][n]), int(g["y"][n]), int(g["vis"][n])) for n in range(T)}
+    parts = [{n: xyv[n] for n in range(0, T // 3)}, {n: xyv[n] for n in range(T // 3, T)}]  # two "ranks"
+    TrackingRunner._assemble(bt, parts, T)
+    got = bt.results.predictions
+    assert [int(b.xy[0]) for b in got] == g["X"].tolist() and [int(b.xy[1]) for b in got] == g["Y"].tolist()
+    assert [b.visibility for b in got] == g["V"].tolist()
+    # a tracker without an inpainting model keeps the TrackNet trajectory
+    bt.inpaintnet = None
+    TrackingRunner._assemble(bt, parts, T)
+    assert [(int(b.xy[0]), int(b.xy[1]), b.visibility) for b in bt.results.predictions] == [xyv[n] for n in range(T)]
