@@ -206,7 +206,10 @@ def main():
 
     import torch.distributed as dist
 
-    from oracle import weights as OW  # seeded synthetic checkpoints only (no real weights exist offline)
+    # The only oracle import of the product arm: it CONSTRUCTS the seeded synthetic checkpoints (a stand-in for
+    # torch.load of real .pt files, none of which exist offline) before anything is timed.  No oracle code computes
+    # anything inside the warm-up or timed regions; the trackers below run on libpadel_b200.so only.
+    from oracle import weights as OW
     from padel_analytics_b200 import _lib as L
     from padel_analytics_b200 import synth
     from padel_analytics_b200.engine import ops

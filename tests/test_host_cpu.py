@@ -241,3 +241,14 @@ def test_runner_assemble_applies_inpainting_after_merging_shards():
     bt.inpaintnet = None
     TrackingRunner._assemble(bt, parts, T)
     assert [(int(b.xy[0]), int(b.xy[1]), b.visibility) for b in bt.results.predictions] == [xyv[n] for n in range(T)]
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under padel_analytics_b200/ may import it (static check)."""
+    root = Path(__file__).resolve().parents[1] / "padel_analytics_b200"
+    bad = []
+    for p in root.rglob("*.py"):
+        for i, line in enumerate(p.read_text().splitlines(), 1):
+            if re.match(r"\s*(from|import)\s+oracle\b", line):
+                bad.append(f"{p.relative_to(root)}:{i}: {line.strip()}")
+    assert not bad, bad
