@@ -252,3 +252,40 @@ def test_product_package_never_imports_the_oracle():
             if re.match(r"\s*(from|import)\s+oracle\b", line):
                 bad.append(f"{p.relative_to(root)}:{i}: {line.strip()}")
     assert not bad, bad
+
+
+def test_yolo_results_scaling_matches_oracle_ops():
+    """YoloEngine._results (product host code: un-letterbox, clip, keypoint-confidence zeroing) against the oracle's
+    restatement of ultralytics scale_boxes / scale_coords on random detections, several geometries."""
+    from oracle import yolov8 as OY
+    from padel_analytics_b200.engine.yolo_engine import YoloEngine
+
+    eng = object.__new__(YoloEngine)  # host logic only; no CUDA here
+    eng.names = {0: "person"}
+    rng = np.random.default_rng(7)
+    for kpt_shape, net_hw, orig_hw in [(None, (384, 640), (1080, 1920)), ((13, 3), (1280, 1280), (1280, 1280)),
+                                       ((12, 3), (640, 640), (640, 640)), ((13, 3), (384, 640), (2160, 3840)),
+                                       (None, (640, 480), (700, 500))]:
+        eng.kpt_shape = kpt_shape
+        K, D = kpt_shape if kpt_shape else (0, 0)
+        n, cap = 3, 9
+        rows = np.zeros((n, cap, 6 + K * D), np.float32)
+        counts = np.array([cap, 4, 0], np.int32)
+        rows[..., 0:4] = rng.uniform(-20, max(net_hw) + 20, (n, cap, 4))
+        rows[..., 4] = rng.uniform(0.3, 1, (n, cap))
+        if K:
+            kp = rng.uniform(-30, max(net_hw) + 30, (n, cap, K, D)).astype(np.float32)
+            kp[..., 2] = rng.uniform(0, 1, (n, cap, K))
+            rows[..., 6:] = kp.reshape(n, cap, -1)
+        res = eng._results(rows, counts, n, net_hw, orig_hw)
+        for i in range(n):
+            c = counts[i]
+            exp_box = OY.scale_boxes(net_hw, torch.from_numpy(rows[i, :c, :4].copy()), orig_hw)
+            assert torch.equal(res[i].boxes.xyxy, exp_box), (kpt_shape, net_hw, orig_hw)
+            assert torch.equal(res[i].boxes.conf, torch.from_numpy(rows[i, :c, 4]))
+            if K:
+                k = torch.from_numpy(rows[i, :c, 6:].reshape(c, K, D).copy())
+                exp_k = OY.scale_coords(net_hw, k, orig_hw)
+                exp_xy = exp_k[..., :2].clone()
+                exp_xy[exp_k[..., 2] < 0.5] = 0
+                assert torch.equal(res[i].keypoints.xy, exp_xy), (kpt_shape, net_hw, orig_hw)
