@@ -59,7 +59,7 @@ __device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t row_b
 
 // kPair is a compile-time switch: a kernel that contains cta_group::2 instructions can only be launched as a
 // cluster of two, so the single-CTA and the CTA-pair variants are separate instantiations.
-// kS (sub-tiles) and kSteps (16-element k-steps per channel block) are compile-time so the single-thread UMMA issue
+// kS (sub-tiles) and kSteps (16-element k-steps per channel block) are compile-time so the UMMA issue
 // loop is straight-line code with immediate descriptor offsets.
 template <bool kPair, int kS, int kSteps>
 __global__ void __launch_bounds__(kConvMaxThreads, 1)
@@ -256,7 +256,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ===== epilogue: two groups of 4 warps (2-5, 7-10) alternating tiles; S sub-tiles of 16 rows x 8 columns each
+    // ===== epilogue: up to three groups of 4 warps (2-5, 7-10, 11-14), tiles round-robin; S sub-tiles of 16 rows x 8 columns each
     const int egroup = warp >= 7 ? 1 + ((warp - 7) >> 2) : 0;
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
@@ -369,7 +369,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // ------------------------------------------------------------------------------------------------------------
 
 // Final launch configuration shared by the halo and stem set-ups: two CTAs per SM when the tile fits in half an SM's
-// shared memory and 256 TMEM columns (light n-scale YOLO layers), else one CTA per SM with two epilogue groups.
+// shared memory and 256 TMEM columns (light n-scale YOLO layers), else one CTA per SM with up to three epilogue groups.
 static void halo_finish_config(ConvPlan* plan) {
   ConvKParams& kp = plan->kp;
   const size_t need = (size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes + sizeof(HaloSmemTail) + 1024;

@@ -8,9 +8,11 @@
 //   tap is again a dense box.  The box lands in shared memory directly in the UMMA K-major swizzled layout
 //   (one pixel = one KB*2-byte row; swizzle 32/64/128B == row size).
 // * B (weights, fp16 [tap][cout][cin]) is fetched by TMA the same way.
-// * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (single thread), warps 2-5 = epilogue
-//   (tcgen05.ld TMEM -> regs -> bias/act/residual -> global).  Accumulators are double-buffered in TMEM so the
-//   epilogue of tile i overlaps the MMAs of tile i+1.  Persistent CTAs, one per SM, static tile striding.
+// * warp 0 = TMA producer (activations), warp 6 = TMA producer (weights), warp 1 = tcgen05.mma issuer (whole warp on
+//   warp-uniform values, elect.sync-predicated instructions), warps 2-5 / 7-10 / 11-14 = up to three epilogue groups
+//   taking tiles round-robin (tcgen05.ld TMEM -> regs -> bias/act/residual -> global).  Up to 8 accumulator sets in
+//   TMEM so the epilogues of tiles i-2..i overlap the MMAs of tile i+1.  Persistent CTAs (one per SM, or two for
+//   light layers), static tile striding, tile coordinates via fast division.
 //
 // Replaces: ultralytics Conv/C2f/Bottleneck/Detect convs (3P) and TrackNet Conv2DBlock
 // (/root/reference/trackers/ball_tracker/models.py:5-17) with BN folded into weight/bias.
@@ -189,7 +191,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ============ epilogue: two groups of 4 warps (2-5 and 7-10), alternating tiles; one TMEM lane quarter per warp
+    // ============ epilogue: up to three groups of 4 warps (2-5, 7-10, 11-14), tiles round-robin; one TMEM lane quarter per warp
     const int egroup = warp >= 7 ? 1 + ((warp - 7) >> 2) : 0;
     const int quarter = warp & 3;
     const int p = quarter * 32 + lane;  // row of the M=128 tile handled by this thread
