@@ -390,4 +390,90 @@ __device__ __forceinline__ void epilogue_fast_staged(const ConvKParams& kp, cons
 }
 #endif  // PB_EXPERIMENTAL_STAGED_EPILOGUE
 
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+// ------------------------------------------------------------------------------------------------------------
+// Bulk-store epilogue (EXPERIMENTAL, compiled out by default; not yet validated on hardware).
+// Each epilogue warp owns 32 pixels of a sub-tile (4 rows x 8 columns).  Per slab of `cb` channels (64 / 32 / 16) it
+// writes the activated fp16 values into a private shared-memory tile [32 pixels][cb] in the TMA swizzle pattern
+// (16-byte unit u of row l goes to u ^ f(l), conflict-free), then one lane issues a single cp.async.bulk.tensor store
+// of the box (cb, 8, 1, 4, 1); the TMA unit clips ragged tiles.  Two tiles per warp, reuse guarded by
+// cp.async.bulk.wait_group.read 1.  Takes the LSU out of the store path.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bulk_swz(int l, int cb) {
+  return cb == 64 ? (uint32_t)(l & 7) : (cb == 32 ? (uint32_t)((l >> 1) & 3) : (uint32_t)((l >> 2) & 1));
+}
+
+// `x0`, `y0`, `n`: output coordinates of the warp's first pixel of sub-tile 0 (column of sub-tile j = x0 + 8 j).
+__device__ __forceinline__ void epilogue_bulk(const ConvKParams& kp, const CUtensorMap* tmap_out, uint32_t t_addr0, int S,
+                                              uint32_t sub_cols, const float* __restrict__ sbias,
+                                              const __half* rp0, size_t sub_res, uint32_t valid_mask, char* stage,
+                                              int x0, int y0, int n, uint32_t& toggle) {
+  uint32_t ra[16], rb[16];
+  const int act = kp.act;
+  const bool has_res = kp.res != nullptr;
+  const bool plain_silu = (kp.dbg_flags & 1) == 0;
+  const int lane = threadIdx.x & 31;
+  const int cb = kp.bulk_cb, cpc = cb >> 4;  // chunks per slab
+  const int nch = kp.cout_store >> 4;
+  const uint32_t sw = bulk_swz(lane, cb);
+  tmem_ld16(t_addr0, ra);
+  for (int j = 0; j < S; ++j) {
+    const bool valid = ((valid_mask >> j) & 1u) != 0;
+    const __half* rpj = rp0 + (size_t)j * sub_res;
+    const uint32_t t_j = t_addr0 + (uint32_t)j * sub_cols;
+    for (int c0 = 0; c0 < nch; c0 += cpc) {
+      char* buf = stage + toggle * 4096;
+      // the store issued two slabs ago read this buffer: wait until it has
+      if (lane == 0) bulk_wait_group_read<1>();
+      __syncwarp();
+      char* wrow = buf + lane * (cb * 2);
+      int jn = j, cn0 = c0 + cpc;
+      if (cn0 >= nch) {
+        cn0 = 0;
+        ++jn;
+      }
+      const bool more_groups = jn < S;
+      const uint32_t t_next = t_addr0 + (uint32_t)jn * sub_cols + (uint32_t)(cn0 * 16);
+#define PB_EPI_BSTAGE(s, cur, nxt)                                                                       \
+  if (s < cpc) {                                                                                         \
+    const int c = c0 + s;                                                                                \
+    uint4 rv[2] = {};                                                                                    \
+    if (has_res && valid) {                                                                              \
+      const uint4* rp = reinterpret_cast<const uint4*>(rpj + c * 16);                                    \
+      rv[0] = __ldg(rp);                                                                                 \
+      rv[1] = __ldg(rp + 1);                                                                             \
+    }                                                                                                    \
+    tmem_ld_wait16(cur);                                                                                 \
+    bool deferred = false;                                                                               \
+    if (s + 1 < cpc) tmem_ld16(t_j + (uint32_t)((c + 1) * 16), nxt);                                     \
+    else if (more_groups) {                                                                              \
+      if ((s & 1) == 1) tmem_ld16(t_next, nxt);                                                          \
+      else deferred = true;                                                                              \
+    }                                                                                                    \
+    float v[16];                                                                                         \
+    epi_compute16(act, has_res, plain_silu, cur, sbias + c * 16, rv, v);                                 \
+    if (deferred) tmem_ld16(t_next, cur);                                                                \
+    uint4 pk[2];                                                                                         \
+    __half2* h2 = reinterpret_cast<__half2*>(pk);                                                        \
+    _Pragma("unroll") for (int q = 0; q < 8; ++q) h2[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);    \
+    *reinterpret_cast<uint4*>(wrow + (((uint32_t)(2 * s) ^ sw) << 4)) = pk[0];                           \
+    *reinterpret_cast<uint4*>(wrow + (((uint32_t)(2 * s + 1) ^ sw) << 4)) = pk[1];                       \
+  }
+      PB_EPI_BSTAGE(0, ra, rb)
+      PB_EPI_BSTAGE(1, rb, ra)
+      PB_EPI_BSTAGE(2, ra, rb)
+      PB_EPI_BSTAGE(3, rb, ra)
+#undef PB_EPI_BSTAGE
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA unit
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_5d(tmap_out, buf, kp.out_coff + c0 * 16, x0 + 8 * j, 0, y0, n);
+        bulk_commit_group();
+      }
+      toggle ^= 1u;
+    }
+  }
+}
+#endif  // PB_EXPERIMENTAL_TMA_STORE
+
 }  // namespace pb

@@ -64,6 +64,9 @@ __device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t row_b
 template <bool kPair, int kS, int kSteps>
 __global__ void __launch_bounds__(kConvMaxThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+                 const __grid_constant__ CUtensorMap tmap_out,
+#endif
                  const __grid_constant__ ConvKParams kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -262,6 +265,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int m = quarter * 32 + lane;
     const int row = m >> 3, col = m & 7;
     const bool fast = epilogue_fast_ok(kp);
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+    uint32_t bulk_toggle = 0;
+    if (kp.bulk_cb != 0 && lane == 0) tma_prefetch_desc(&tmap_out);
+#endif
     int seq = egroup, acc = egroup;  // sequence number / accumulator stage / phase by counters (egroups <= acc_stages)
     uint32_t acc_ph = 0;
     for (int tile = cta0 + egroup * cstride; egroup < kp.egroups && tile < kp.total_tiles;
@@ -292,6 +299,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * kp.acc_cols);
         char* obase = reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)kp.out_coff * esz;
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+        if (kp.bulk_cb != 0)
+          epilogue_bulk(kp, &tmap_out, t0, S, (uint32_t)kp.acc_cols, tail->bias, kp.res + pix0 * kp.res_C + kp.res_coff,
+                        (size_t)8 * kp.res_C, vm,
+                        reinterpret_cast<char*>(smem) + kp.epi_stage_off + (egroup * 4 + quarter) * 8192,
+                        t.tw * 8 * S, t.th * 16 + 4 * quarter, t.n, bulk_toggle);
+        else
+#endif
 #ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE
         if (kp.epi_stage_off != 0 && eo.mode != PB_OUT_F32_NHWC && kp.cout_store >= 32)
           epilogue_fast_staged(kp, eo, t0, S, (uint32_t)kp.acc_cols, kp.cout_store >> 4, tail->bias, obase,
@@ -351,6 +366,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         acc_ph ^= 1u;
       }
     }
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+    if (kp.bulk_cb != 0 && lane == 0) bulk_wait_group<0>();  // the last bulk stores must have left shared memory and landed
+#endif
   }
 
   tc_fence_before();
@@ -697,7 +715,41 @@ int conv_halo_s2_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn enco
   return 0;
 }
 
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+typedef void (*HaloKernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, ConvKParams);
+
+// Bulk-store epilogue set-up: output tensor map + two 4 KB staging tiles per epilogue warp behind the tail.
+// Enabled by PADEL_B200_CONV_DEBUG bit 3 for plain fp16 NHWC stores of single-CTA layers when the tiles fit.
+int conv_halo_out_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode) {
+  ConvKParams& kp = plan->kp;
+  kp.bulk_cb = 0;
+  if ((kp.dbg_flags & 8) == 0 || d->out_mode != PB_OUT_F16_NHWC || kp.pair || d->head_n != 0 ||
+      (d->cout_store & 15) != 0 || ((d->out_C | d->out_coff) & 7) != 0)
+    return 0;
+  const int cb = d->cout_store % 64 == 0 ? 64 : (d->cout_store % 32 == 0 ? 32 : 16);
+  const size_t tail_end = ((size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes + sizeof(HaloSmemTail) +
+                           4095) & ~(size_t)4095;  // 4 KB aligned: the swizzle pattern is on absolute address bits
+  const size_t stage_bytes = (size_t)kp.egroups * 4 * 8192;
+  const bool occ2 = plan->threads == 224;
+  if (tail_end + stage_bytes + 1024 > (occ2 ? (size_t)112 * 1024 : (size_t)227 * 1024)) return 0;
+  const cuuint64_t C = (cuuint64_t)d->out_C, W = (cuuint64_t)kp.Wo, H = (cuuint64_t)kp.Ho;
+  cuuint64_t dims[5] = {C, W, 1, H, (cuuint64_t)d->N};
+  cuuint64_t strides[4] = {C * 2, W * C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)cb, 8, 1, 4, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(&plan->tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, d->out, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PB_CHECK(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+  kp.bulk_cb = cb;
+  kp.epi_stage_off = (uint32_t)tail_end;
+  if (plan->smem_bytes < tail_end + stage_bytes + 1024) plan->smem_bytes = tail_end + stage_bytes + 1024;
+  return 0;
+}
+#else
 typedef void (*HaloKernelFn)(CUtensorMap, CUtensorMap, ConvKParams);
+#endif
 
 template <bool kPair>
 static HaloKernelFn halo_kernel_for(int S, int steps) {
@@ -740,7 +792,11 @@ int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, plan->tmap_a, plan->tmap_w, plan->tmap_out, plan->kp);
+#else
   cudaError_t le = cudaLaunchKernelEx(&cfg, fn, plan->tmap_a, plan->tmap_w, plan->kp);
+#endif
   if (le == cudaSuccess) le = cudaGetLastError();
   PB_CHECK(le == cudaSuccess,
            "conv(halo): launch failed: %s (pair %d, grid %d, threads %d, smem %zu, tiles %d, S %d, BN %d, KB %d)",

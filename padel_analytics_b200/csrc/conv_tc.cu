@@ -390,6 +390,12 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     kp.dbg_flags = df ? atoi(df) : 0;
   }
   plan->variant = 0;
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+  if (stem) {
+    const int rc = conv_stem_setup(d, plan, encode);
+    return rc == 0 ? conv_halo_out_setup(d, plan, encode) : rc;
+  }
+#endif
   if (stem) return conv_stem_setup(d, plan, encode);
   {
     // halo variant for 3x3/s1 layers: default on for cout <= 192 (the layers the per-tap kernel leaves
@@ -398,6 +404,9 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     const int mode = e ? atoi(e) : 2;
     if (mode == 1 || (mode == 2 && d->cout_pad <= 192)) {
       const int rc = d->stride == 2 ? conv_halo_s2_setup(d, plan, encode) : conv_halo_setup(d, plan, encode);
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+      if (rc == 0) return conv_halo_out_setup(d, plan, encode);
+#endif
       if (rc >= 0) return rc;
     }
   }

@@ -82,6 +82,10 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int kPending>
+__device__ __forceinline__ void bulk_wait_group() {  // the stores themselves have completed
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
+}
+template <int kPending>
 __device__ __forceinline__ void bulk_wait_group_read() {  // smem of all but the newest kPending groups may be reused
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
 }
