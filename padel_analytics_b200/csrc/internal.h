@@ -114,7 +114,9 @@ struct ConvKParams {
   int hs_ntaps, hs_sbo_rows, hs_x0, hs_y0, hs_tile_h;  // taps served from the halo, 8-row group stride (rows), box origin offsets
   int hs_tap_off[9];                                   // smem row offset of each tap's first pixel
   int hs_tap_desc[9];                                  // the same in 16-byte descriptor units (offset * row_bytes / 16)
-  int bulk_cb;             // PB_EXPERIMENTAL_TMA_STORE: channels per bulk-store slab (64 / 32 / 16), 0 = direct stores
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+  int bulk_cb;             // channels per bulk-store slab (64 / 32 / 16), 0 = direct stores
+#endif
   uint32_t epi_stage_off;  // byte offset (from the aligned smem base) of the per-warp 4 KB store-staging tiles; 0 = off
   int dbg_flags;   // PADEL_B200_CONV_DEBUG: bit0 = paired-reciprocal SiLU, bit1 = no fast epilogue, bit2 = staged (transposed) stores, bit3 = bulk (TMA) stores
   long long* dbg;  // optional timeline buffer (CTA 0, first 64 tiles): [role 0..2][64][4] clock64 stamps
