@@ -22,6 +22,10 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
 ]
+# bring-up only: PADEL_B200_EXPERIMENTAL=tma_store,staged compiles the experimental epilogues in;
+# the product build defines neither
+for _x in filter(None, os.environ.get("PADEL_B200_EXPERIMENTAL", "").split(",")):
+    NVCC_FLAGS.append({"tma_store": "-DPB_EXPERIMENTAL_TMA_STORE", "staged": "-DPB_EXPERIMENTAL_STAGED_EPILOGUE"}[_x])
 
 
 def _nvcc() -> str:

@@ -403,18 +403,18 @@ __device__ __forceinline__ uint32_t bulk_swz(int l, int cb) {
   return cb == 64 ? (uint32_t)(l & 7) : (cb == 32 ? (uint32_t)((l >> 1) & 3) : (uint32_t)((l >> 2) & 1));
 }
 
-// `x0`, `y0`, `n`: output coordinates of the warp's first pixel of sub-tile 0 (column of sub-tile j = x0 + 8 j).
+// `x0`, `y0`, `n`: output coordinates of the warp's first pixel of sub-tile 0 (column of sub-tile j = x0 + 8 j);
+// `ch_base`: first output channel of this N tile in the output tensor, `nch`: its 16-channel chunks.
 __device__ __forceinline__ void epilogue_bulk(const ConvKParams& kp, const CUtensorMap* tmap_out, uint32_t t_addr0, int S,
                                               uint32_t sub_cols, const float* __restrict__ sbias,
                                               const __half* rp0, size_t sub_res, uint32_t valid_mask, char* stage,
-                                              int x0, int y0, int n, uint32_t& toggle) {
+                                              int x0, int y0, int n, int ch_base, int nch, uint32_t& toggle) {
   uint32_t ra[16], rb[16];
   const int act = kp.act;
   const bool has_res = kp.res != nullptr;
   const bool plain_silu = (kp.dbg_flags & 1) == 0;
   const int lane = threadIdx.x & 31;
   const int cb = kp.bulk_cb, cpc = cb >> 4;  // chunks per slab
-  const int nch = kp.cout_store >> 4;
   const uint32_t sw = bulk_swz(lane, cb);
   tmem_ld16(t_addr0, ra);
   for (int j = 0; j < S; ++j) {
@@ -467,7 +467,7 @@ __device__ __forceinline__ void epilogue_bulk(const ConvKParams& kp, const CUten
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA unit
       __syncwarp();
       if (lane == 0) {
-        tma_store_5d(tmap_out, buf, kp.out_coff + c0 * 16, x0 + 8 * j, 0, y0, n);
+        tma_store_5d(tmap_out, buf, ch_base + c0 * 16, x0 + 8 * j, 0, y0, n);
         bulk_commit_group();
       }
       toggle ^= 1u;

@@ -304,7 +304,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           epilogue_bulk(kp, &tmap_out, t0, S, (uint32_t)kp.acc_cols, tail->bias, kp.res + pix0 * kp.res_C + kp.res_coff,
                         (size_t)8 * kp.res_C, vm,
                         reinterpret_cast<char*>(smem) + kp.epi_stage_off + (egroup * 4 + quarter) * 8192,
-                        t.tw * 8 * S, t.th * 16 + 4 * quarter, t.n, bulk_toggle);
+                        t.tw * 8 * S, t.th * 16 + 4 * quarter, t.n, kp.out_coff, kp.cout_store >> 4, bulk_toggle);
         else
 #endif
 #ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE

@@ -50,6 +50,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& kp, int tile
 
 __global__ void __launch_bounds__(kConvMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+               const __grid_constant__ CUtensorMap tmap_out,
+#endif
                const __grid_constant__ ConvKParams kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B alignment is required by the 128B swizzle pattern; align explicitly (the launch adds 1 KB of slack).
@@ -200,6 +203,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int th_i = (p >> kp.tw_log2) & THm;
     const int tn_i = p >> (kp.tw_log2 + kp.th_log2);
     const bool fast = epilogue_fast_ok(kp);
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+    uint32_t bulk_toggle = 0;
+    if (kp.bulk_cb != 0 && lane == 0) tma_prefetch_desc(&tmap_out);
+    const int m0 = quarter * 32;  // the warp's 32 pixels start here inside the (TN x TH x TW) tile
+    const int bx0 = m0 & TWm, by0 = (m0 >> kp.tw_log2) & THm, bn0 = m0 >> (kp.tw_log2 + kp.th_log2);
+#endif
     // per-CTA tile sequence number / accumulator stage / phase advance by counters (egroups <= acc_stages)
     int seq = egroup, acc = egroup;
     uint32_t acc_phase = 0;
@@ -237,6 +246,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           char* obase = reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)(kp.out_coff + tc.nt * kp.BN) * esz;
           const __half* rbase = kp.res + px.pix * kp.res_C + kp.res_coff + tc.nt * kp.BN;
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+          if (kp.bulk_cb != 0)
+            epilogue_bulk(kp, &tmap_out, t_addr, 1, 0u, sb, rbase, 0, px.valid ? 1u : 0u,
+                          reinterpret_cast<char*>(smem) + kp.epi_stage_off + (egroup * 4 + quarter) * 8192,
+                          (tc.tw << kp.tw_log2) + bx0, (tc.th << kp.th_log2) + by0,
+                          tc.tn * (128 >> (kp.tw_log2 + kp.th_log2)) + bn0, kp.out_coff + tc.nt * kp.BN, cn >> 4,
+                          bulk_toggle);
+          else
+#endif
 #ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE
           if (kp.epi_stage_off != 0 && eo.mode != PB_OUT_F32_NHWC && cn >= 32 && (cn & 15) == 0)
             epilogue_fast_staged(kp, eo, t_addr, 1, 0u, cn >> 4, sb, obase, rbase, 0, 0, px.valid ? 1u : 0u,
@@ -283,6 +301,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         acc_phase ^= 1u;
       }
     }
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+    if (kp.bulk_cb != 0 && lane == 0) bulk_wait_group<0>();  // the last bulk stores must have left shared memory and landed
+#endif
   }
 
   tc_fence_before();
@@ -504,6 +525,36 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     }
   }
 
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+  // bulk-store epilogue (PADEL_B200_CONV_DEBUG bit 3): output tensor map whose box is one epilogue warp's 32 pixels
+  kp.bulk_cb = 0;
+  if ((kp.dbg_flags & 8) != 0 && d->out_mode == PB_OUT_F16_NHWC && d->head_n == 0 && (d->cout_store & 15) == 0 &&
+      ((d->out_C | d->out_coff) & 7) == 0 && (kp.n_ntiles == 1 || d->cout_store == d->cout_pad)) {
+    int cb = 64;
+    while (cb > 16 && (kp.BN % cb != 0 || d->cout_store % cb != 0)) cb >>= 1;
+    const size_t tail_end = ((size_t)stages * stage_bytes + sizeof(ConvSmemTail) + 4095) & ~(size_t)4095;
+    const size_t stg = (size_t)kp.egroups * 4 * 8192;
+    if (tail_end + stg + 1024 <= (occ2 ? (size_t)112 * 1024 : (size_t)227 * 1024)) {
+      const int bw = TW < 32 ? TW : 32;
+      const int bh = TH < 32 / bw ? TH : 32 / bw;
+      const int bn = 32 / (bw * bh);
+      const cuuint64_t C = (cuuint64_t)d->out_C, W = (cuuint64_t)kp.Wo, H = (cuuint64_t)kp.Ho;
+      cuuint64_t dims[5] = {C, W, 1, H, (cuuint64_t)d->N};
+      cuuint64_t strides[4] = {C * 2, W * C * 2, W * C * 2, H * W * C * 2};
+      cuuint32_t box[5] = {(cuuint32_t)cb, (cuuint32_t)bw, 1, (cuuint32_t)bh, (cuuint32_t)bn};
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      CUresult r = encode(&plan->tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, d->out, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : (cb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      PB_CHECK(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+      kp.bulk_cb = cb;
+      kp.epi_stage_off = (uint32_t)tail_end;
+      if (plan->smem_bytes < tail_end + stg + 1024) plan->smem_bytes = tail_end + stg + 1024;
+    }
+  }
+#endif
   const CUtensorMapSwizzle swz = kp.KB == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : kp.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -558,7 +609,12 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   PB_CHECK(attr_err == cudaSuccess, "conv: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
+#ifdef PB_EXPERIMENTAL_TMA_STORE
+  conv_tc_kernel<<<plan->grid, plan->threads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->tmap_out,
+                                                                          plan->kp);
+#else
   conv_tc_kernel<<<plan->grid, plan->threads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->kp);
+#endif
   PB_CUDA(cudaGetLastError());
   count_launch();
   return 0;
