@@ -374,7 +374,6 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
   if (d->res) {
     PB_CHECK(d->res_C % 8 == 0 && d->res_coff % 8 == 0 && (reinterpret_cast<uintptr_t>(d->res) & 15) == 0,
              "conv: residual must be 16-byte aligned slices");
-    PB_CHECK(d->cout_store % 16 == 0 || true, "unreachable");
   }
   EncodeTiledFn encode = get_encode_fn();
   PB_CHECK(encode != nullptr, "conv: cuTensorMapEncodeTiled not available (no CUDA driver?)");
