@@ -124,7 +124,12 @@ class FusedPass:
 
     def run(self, batches: Iterable):
         """batches: iterable of uint8 (n,H,W,3) BGR batches (pinned host tensors, device tensors or lists of frames),
-        n <= batch_size.  Yields one {tracker name: results} dict per batch."""
+        n <= batch_size.  Yields one {tracker name: results} dict per batch.
+
+        One batch of look-ahead: batch i+1 is pulled from `batches` and enqueued before batch i's results are yielded.
+        Host batches are copied into internal staging slots, so their memory is free once the next batch has been
+        pulled; a DEVICE tensor passed as a batch is read in place and must stay untouched until the results of the
+        batch after it have been yielded (rotate three buffers, or pass host batches)."""
         it = iter(batches)
         main = torch.cuda.current_stream()
 
