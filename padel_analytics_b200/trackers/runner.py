@@ -127,9 +127,8 @@ class FusedPass:
         n <= batch_size.  Yields one {tracker name: results} dict per batch.
 
         One batch of look-ahead: batch i+1 is pulled from `batches` and enqueued before batch i's results are yielded.
-        Host batches are copied into internal staging slots, so their memory is free once the next batch has been
-        pulled; a DEVICE tensor passed as a batch is read in place and must stay untouched until the results of the
-        batch after it have been yielded (rotate three buffers, or pass host batches)."""
+        A batch (pinned host tensor: copied asynchronously into a staging slot; device tensor: read in place) must stay
+        untouched until ITS OWN results have been yielded, i.e. a producer that reuses buffers needs at least two."""
         it = iter(batches)
         main = torch.cuda.current_stream()
 
