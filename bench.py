@@ -157,7 +157,7 @@ def run_reference_arm(args, rank, world):
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -184,7 +184,13 @@ def build_trackers(B, hw, ckpts, dev):
     return tr, med
 
 
+# The contract is ONE JSON line on stdout: everything else this process prints (tracker banners, library chatter)
+# is sent to stderr, the JSON line goes to the real stdout.
+JSON_OUT = sys.stdout
+
+
 def main():
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -382,7 +388,7 @@ def main():
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(max(ms_e2e, wall_e2e * 1e3) / args.steps, 3)},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-        }))
+        }), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
