@@ -289,3 +289,47 @@ def test_yolo_results_scaling_matches_oracle_ops():
                 exp_xy = exp_k[..., :2].clone()
                 exp_xy[exp_k[..., 2] < 0.5] = 0
                 assert torch.equal(res[i].keypoints.xy, exp_xy), (kpt_shape, net_hw, orig_hw)
+
+
+def test_weight_folding_and_packing_layouts():
+    """engine/ops.py host helpers: BN folding is the exact conv+BN(eval) algebra; packed layouts are
+    [tap][cout_pad][cin_pad] (with an optional input-channel map) and, for the stem, [filter row][cout_pad][s*4 + c]."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from padel_analytics_b200.engine import ops
+
+    g = torch.Generator().manual_seed(0)
+    conv = nn.Conv2d(5, 7, 3, padding=1, bias=False)
+    bn = nn.BatchNorm2d(7, eps=1e-3).eval()
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g))
+        bn.weight.copy_(torch.rand(7, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(7, generator=g))
+        bn.running_mean.copy_(torch.randn(7, generator=g))
+        bn.running_var.copy_(torch.rand(7, generator=g) + 0.5)
+        x = torch.randn(2, 5, 9, 11, generator=g)
+        w, b = ops.fold_bn(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, 1e-3)
+        assert torch.allclose(F.conv2d(x, w, b, padding=1), bn(conv(x)), atol=1e-5)
+    wp, bp = ops.pack_conv_weight(w, b, 16, 16, "cpu")
+    assert wp.shape == (9, 16, 16) and wp.dtype == torch.float16 and bp.shape == (16,)
+    for r in range(3):
+        for s in range(3):
+            assert torch.equal(wp[r * 3 + s, :7, :5], w[:, :, r, s].half())
+    assert torch.count_nonzero(wp[:, 7:]) == 0 and torch.count_nonzero(wp[:, :, 5:]) == 0
+    assert torch.equal(bp[:7], b.float()) and torch.count_nonzero(bp[7:]) == 0
+    # input-channel map (concat of individually padded slices): logical channel i lives at cin_map[i]
+    cmap = [0, 1, 2, 16, 17]
+    wm, _ = ops.pack_conv_weight(w, b, 32, 16, "cpu", cin_map=cmap)
+    for i, pos in enumerate(cmap):
+        assert torch.equal(wm[4, :7, pos], w[:, i, 1, 1].half())
+    assert torch.count_nonzero(wm[:, :, 3:16]) == 0
+    # stem: k = s*4 + c over the padded 4-channel pixels, fourth pixel / fourth channel carry zero weights
+    ws = torch.randn(6, 3, 3, 3, generator=g)
+    sp, sb = ops.pack_stem_weight(ws, torch.arange(6.0), 16, "cpu")
+    assert sp.shape == (3, 16, 16)
+    for r in range(3):
+        for s in range(3):
+            for c in range(3):
+                assert torch.equal(sp[r, :6, s * 4 + c], ws[:, c, r, s].half())
+    assert torch.count_nonzero(sp[:, :, 3::4]) == 0 and torch.count_nonzero(sp[:, :, 12:]) == 0
+    assert torch.equal(sb[:6], torch.arange(6.0))
