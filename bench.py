@@ -384,7 +384,8 @@ def main():
                        "global_batch": B * world, "l2": "inputs (199 MB/batch) and activations exceed L2; no flush",
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
                        "detections_in_timed_region": ndet,
-                       "pass": "fused single pass: one upload per batch shared by the four trackers"},
+                       "pass": "fused single pass: one upload per batch shared by the four trackers, one batch of "
+                               "look-ahead, YOLO chains on their own streams"},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(max(ms_e2e, wall_e2e * 1e3) / args.steps, 3)},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
