@@ -162,6 +162,13 @@ int pb_yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count
 int pb_inpaintnet_forward(const float* coor, const float* mask, int N, int L, const float* weights, float* out,
                           void* stream);
 
+/* ---- TrackNet background median (ball_tracker/iterable.py:58-81) ------------------------------------------- */
+/* Per-byte temporal median of T frames: frames u8 (T, frame_bytes) contiguous on the device (frame_bytes % 4 == 0),
+ * out u8 (frame_bytes) = np.median(frames, 0).astype(uint8), i.e. (s[(T-1)/2] + s[T/2]) >> 1 per byte position.
+ * swap_rb != 0: the frames are 3-channel BGR pixels and the median is written in RGB order (the reference converts
+ * every frame BGR->RGB before np.median, iterable.py:63).                                                        */
+int pb_median_u8(const uint8_t* frames, int T, long long frame_bytes, uint8_t* out, int swap_rb, void* stream);
+
 /* ---- TrackNet post-processing (ball_tracker.py:449-509 ; predict.py:7-39) ---------------------------------- */
 /* Temporal ensemble + >thr. pred: float (S,8,H,W) raw heat-maps of consecutive windows; window index of pred[0]
  * is `first_window`; frames [frame0, frame0+nframes) are produced; total_windows = total_frames-7.

@@ -7,8 +7,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libpadel_b200.so"
+# PADEL_B200_LIB: load another build of the same ABI (bring-up A/B of experimental kernels); default = the product lib
+LIB_PATH = Path(os.environ["PADEL_B200_LIB"]).resolve() if os.environ.get("PADEL_B200_LIB") else _HERE / "libpadel_b200.so"
 
 
 class PbError(RuntimeError):
@@ -64,6 +67,7 @@ SIGNATURES = {
     "pb_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _i, _p]),
     "pb_yolo_nms": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p, _p]),
     "pb_inpaintnet_forward": (_i, [_p, _p, _i, _i, _p, _p, _p]),
+    "pb_median_u8": (_i, [_p, _i, C.c_longlong, _p, _i, _p]),
     "pb_tracknet_ensemble": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p]),
     "pb_ccl_bbox": (_i, [_p, _i, _i, _i, _p, _p, _p]),
 }

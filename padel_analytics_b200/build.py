@@ -24,7 +24,11 @@ NVCC_FLAGS = [
 ]
 # bring-up only: PADEL_B200_EXPERIMENTAL=tma_store,staged compiles the experimental epilogues in;
 # the product build defines neither
-for _x in filter(None, os.environ.get("PADEL_B200_EXPERIMENTAL", "").split(",")):
+_EXP = list(filter(None, os.environ.get("PADEL_B200_EXPERIMENTAL", "").split(",")))
+if _EXP:  # experimental builds never overwrite the product library (load one with PADEL_B200_LIB=<path>)
+    LIB = HERE / "libpadel_b200_exp.so"
+    OBJ = HERE / "build_exp"
+for _x in _EXP:
     NVCC_FLAGS.append({"tma_store": "-DPB_EXPERIMENTAL_TMA_STORE", "staged": "-DPB_EXPERIMENTAL_STAGED_EPILOGUE"}[_x])
 
 

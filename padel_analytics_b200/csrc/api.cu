@@ -31,6 +31,15 @@ int num_sms() {
   return sms;
 }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PADEL_B200_PDL");
+    on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return on != 0;
+}
+
 enum class OpKind { Conv, MaxPool2, Upsample2, SppfPool, PointwiseHead };
 
 struct Op {

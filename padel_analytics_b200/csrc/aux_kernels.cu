@@ -2,6 +2,7 @@
 // All move 16-byte vectors (8 channels) per thread with consecutive threads on consecutive channel groups,
 // so warps read/write contiguous NHWC runs.
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace pb {
 
@@ -20,6 +21,8 @@ __global__ void maxpool2_kernel(const __half* __restrict__ in, int N, int H, int
                                 __half* __restrict__ out, int out_C, int out_coff) {
   const int Ho = H / 2, Wo = W / 2;
   const long total = (long)N * Ho * Wo * cg;
+  griddep_launch_dependents();
+  griddep_wait();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int g = (int)(i % cg);
     long p = i / cg;
@@ -41,6 +44,8 @@ __global__ void upsample2_kernel(const __half* __restrict__ in, int N, int H, in
                                  __half* __restrict__ out, int out_C, int out_coff) {
   const int Ho = H * 2, Wo = W * 2;
   const long total = (long)N * Ho * Wo * cg;
+  griddep_launch_dependents();
+  griddep_wait();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int g = (int)(i % cg);
     long p = i / cg;
@@ -67,6 +72,8 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(__half* __restrict__ buf
   const int c = cg * 8;
   const int HW = H * W;
   __half* base = buf + (size_t)n * HW * C + g * 8;
+  griddep_launch_dependents();
+  griddep_wait();
   for (int i = threadIdx.x; i < HW; i += blockDim.x) cur[i] = *reinterpret_cast<const uint4*>(base + (size_t)i * C);
   __syncthreads();
   for (int pass = 1; pass <= 3; ++pass) {
@@ -172,9 +179,9 @@ int launch_maxpool2(const void* in, int N, int H, int W, int C, int c_off, int c
            "maxpool2: channel slices must be multiples of 8");
   PB_CHECK(H % 2 == 0 && W % 2 == 0, "maxpool2: odd spatial size");
   const long total = (long)N * (H / 2) * (W / 2) * (c / 8);
-  maxpool2_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __half*>(in), N, H, W, C, c_off,
-                                                       c / 8, reinterpret_cast<__half*>(out), out_C, out_coff);
-  PB_CUDA(cudaGetLastError());
+  PB_CUDA(launch_pdl(maxpool2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, 1,
+                     reinterpret_cast<const __half*>(in), N, H, W, C, c_off, c / 8, reinterpret_cast<__half*>(out), out_C,
+                     out_coff));
   count_launch();
   return 0;
 }
@@ -184,9 +191,9 @@ int launch_upsample2(const void* in, int N, int H, int W, int C, int c_off, int 
   PB_CHECK(c % 8 == 0 && c_off % 8 == 0 && C % 8 == 0 && out_C % 8 == 0 && out_coff % 8 == 0,
            "upsample2: channel slices must be multiples of 8");
   const long total = (long)N * (H * 2) * (W * 2) * (c / 8);
-  upsample2_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __half*>(in), N, H, W, C, c_off,
-                                                        c / 8, reinterpret_cast<__half*>(out), out_C, out_coff);
-  PB_CUDA(cudaGetLastError());
+  PB_CUDA(launch_pdl(upsample2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, 1,
+                     reinterpret_cast<const __half*>(in), N, H, W, C, c_off, c / 8, reinterpret_cast<__half*>(out), out_C,
+                     out_coff));
   count_launch();
   return 0;
 }
@@ -223,8 +230,8 @@ int launch_sppf_pool(void* buf, int N, int H, int W, int C, int c, cudaStream_t 
     PB_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  sppf_pool_kernel<<<N * (c / 8), 256, smem, s>>>(reinterpret_cast<__half*>(buf), N, H, W, C, c / 8);
-  PB_CUDA(cudaGetLastError());
+  PB_CUDA(launch_pdl(sppf_pool_kernel, dim3(N * (c / 8)), dim3(256), smem, s, 1, reinterpret_cast<__half*>(buf), N, H, W,
+                     C, c / 8));
   count_launch();
   return 0;
 }

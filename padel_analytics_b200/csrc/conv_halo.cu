@@ -120,6 +120,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (pair) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
+  // PDL: the prologue above touched constant data only; from here on activations are read and written
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (warp == 0) {
     // ===================== halo producer: one TMA box per (tile, channel block) =====================
@@ -778,26 +781,13 @@ int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
       configured.push_back(reinterpret_cast<const void*>(fn));
     }
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(plan->grid);
-  cfg.blockDim = dim3(plan->threads);
-  cfg.dynamicSmemBytes = plan->smem_bytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  if (kp.pair) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  }
 #ifdef PB_EXPERIMENTAL_TMA_STORE
-  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, plan->tmap_a, plan->tmap_w, plan->tmap_out, plan->kp);
+  cudaError_t le = launch_pdl(fn, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, kp.pair ? 2 : 1,
+                              plan->tmap_a, plan->tmap_w, plan->tmap_out, plan->kp);
 #else
-  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, plan->tmap_a, plan->tmap_w, plan->kp);
+  cudaError_t le = launch_pdl(fn, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, kp.pair ? 2 : 1,
+                              plan->tmap_a, plan->tmap_w, plan->kp);
 #endif
-  if (le == cudaSuccess) le = cudaGetLastError();
   PB_CHECK(le == cudaSuccess,
            "conv(halo): launch failed: %s (pair %d, grid %d, threads %d, smem %zu, tiles %d, S %d, BN %d, KB %d)",
            cudaGetErrorString(le), kp.pair, plan->grid, plan->threads, plan->smem_bytes, kp.total_tiles, kp.hs_S, kp.BN,

@@ -86,6 +86,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
+  // PDL: the prologue above touched constant data only; from here on activations are read and written
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (warp == 0) {
     // ============================== TMA producer: activations ==============================
@@ -609,12 +612,12 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
   });
   PB_CHECK(attr_err == cudaSuccess, "conv: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
 #ifdef PB_EXPERIMENTAL_TMA_STORE
-  conv_tc_kernel<<<plan->grid, plan->threads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->tmap_out,
-                                                                          plan->kp);
+  PB_CUDA(launch_pdl(conv_tc_kernel, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, 1, plan->tmap_a,
+                     plan->tmap_w, plan->tmap_out, plan->kp));
 #else
-  conv_tc_kernel<<<plan->grid, plan->threads, plan->smem_bytes, stream>>>(plan->tmap_a, plan->tmap_w, plan->kp);
+  PB_CUDA(launch_pdl(conv_tc_kernel, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, 1, plan->tmap_a,
+                     plan->tmap_w, plan->kp));
 #endif
-  PB_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }

@@ -48,6 +48,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may start while its predecessor in the stream is still running: everything before griddep_wait() (barrier init,
+// TMEM allocation, tensor-map prefetch, bias staging = constant data only) overlaps the predecessor's tail;
+// griddep_wait() returns once the predecessor has completed and its writes are visible.  griddep_launch_dependents()
+// lets the successor's CTAs be scheduled as SMs free up; it is issued only AFTER this CTA owns its TMEM columns, so a
+// successor CTA can never hold TMEM that a CTA of an earlier grid is still waiting for.  Both are no-ops for
+// kernels launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // TMA tiled loads (global -> shared), completion on an mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

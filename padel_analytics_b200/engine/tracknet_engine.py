@@ -177,14 +177,24 @@ class BallPipeline:
         self._pending = [None] * 3
         self._turn = 0
         self.ens = None
-        # median: full-res RGB -> uint8 -> PIL resize (iterable.py:76-81), on device with the same kernel
-        med = torch.as_tensor(median_rgb)
-        if med.shape[:2] != (self.Hs, self.Ws):
-            raise L.PbError("median must have the frame resolution")
-        med = med.to(torch.uint8).to(self.dev).contiguous().view(1, self.Hs, self.Ws, 3)
         self.median_small = torch.zeros((1, H, W, 4), dtype=torch.float16, device=self.dev)
-        self._resize(med, 1, self.median_small, swap_rb=0)
+        self._median_src = None
+        self.set_median(median_rgb)
         self.reset()
+
+    def set_median(self, median_rgb):
+        """(Re)apply the background: full-res RGB -> uint8 -> PIL resize (iterable.py:76-81), on device with the same
+        kernel as the frames.  A no-op when called again with the very same array object/contents."""
+        med = torch.as_tensor(median_rgb)
+        if tuple(med.shape[:2]) != (self.Hs, self.Ws):
+            raise L.PbError("median must have the frame resolution")
+        med = med.to(torch.uint8)
+        if self._median_src is not None and self._median_src.shape == med.shape and \
+                torch.equal(self._median_src, med.cpu()):
+            return
+        self._median_src = med.cpu().clone()
+        dev_med = med.to(self.dev).contiguous().view(1, self.Hs, self.Ws, 3)
+        self._resize(dev_med, 1, self.median_small, swap_rb=0)
 
     def reset(self, base: int = 0):
         """base = absolute index of the first frame that will be pushed (= first window computed); > 0 for shards

@@ -57,19 +57,28 @@ class Ball(Object):
         return frame
 
 
-def median_background(frames_bgr: list[np.ndarray], device="cuda") -> np.ndarray:
-    """np.median(frames_rgb, 0).astype('uint8') (iterable.py:61-81) computed on device: per-pixel sort over the
-    frame axis; even counts average the two middle values and truncate like the float64 -> uint8 cast."""
-    n = len(frames_bgr)
-    H, W, _ = frames_bgr[0].shape
-    out = torch.empty((H, W, 3), dtype=torch.uint8, device=device)
-    rows = max(1, (256 << 20) // (n * W * 3))
-    for r0 in range(0, H, rows):
-        chunk = torch.from_numpy(np.stack([f[r0:r0 + rows] for f in frames_bgr])).to(device)
-        s, _ = torch.sort(chunk, dim=0)
-        med = (s[(n - 1) // 2].to(torch.int32) + s[n // 2].to(torch.int32)) // 2
-        out[r0:r0 + rows] = med.to(torch.uint8)
-    return out.flip(-1).cpu().numpy()  # BGR -> RGB
+def median_background(frames_bgr, device="cuda") -> np.ndarray:
+    """np.median(frames_rgb, 0).astype('uint8') (iterable.py:58-81) on the device: the frames (list of HWC uint8 BGR
+    arrays, or one (T,H,W,3) uint8 tensor, host or device) are stacked in HBM and `pb_median_u8` selects the per-byte
+    median (even counts: mean of the two middle values, truncated like the reference's float64 -> uint8 cast),
+    writing RGB order.  Returns the (H,W,3) uint8 RGB median on the host."""
+    from .. import _lib as L
+
+    if isinstance(frames_bgr, torch.Tensor):
+        stack = frames_bgr.to(device).contiguous()
+    else:
+        n = len(frames_bgr)
+        H, W, _ = frames_bgr[0].shape
+        stack = torch.empty((n, H, W, 3), dtype=torch.uint8, device=device)
+        step = max(1, (256 << 20) // (H * W * 3))  # upload in ~256 MB pieces
+        for i in range(0, n, step):
+            stack[i:i + step].copy_(torch.from_numpy(np.stack(frames_bgr[i:i + step])))
+    if stack.dtype != torch.uint8 or stack.dim() != 4 or stack.shape[-1] != 3:
+        raise L.PbError("median_background: frames must be uint8 (T,H,W,3)")
+    T, H, W, _ = stack.shape
+    out = torch.empty((H, W, 3), dtype=torch.uint8, device=stack.device)
+    L.check(L.lib().pb_median_u8(stack.data_ptr(), T, H * W * 3, out.data_ptr(), 1, L.stream_ptr()))
+    return out.cpu().numpy()
 
 
 class BallTracker(Tracker):
@@ -129,12 +138,16 @@ class BallTracker(Tracker):
         raise NoPredictSample()
 
     def _pipeline(self, frame_hw, median_rgb) -> BallPipeline:
+        """The pipeline (device rings, resample tables) is cached per frame size; the background median is re-applied
+        on every call, as the reference does per predict_frames call (iterable.py:58-81)."""
         if self._pipe is None or (self._pipe.Hs, self._pipe.Ws) != tuple(frame_hw):
             self._pipe = BallPipeline(self.tracknet, frame_hw, median_rgb)
+        else:
+            self._pipe.set_median(median_rgb)
         return self._pipe
 
     def track_xyv(self, frame_generator: Iterable[np.ndarray], total_frames: int, first_frame: int = 0,
-                  emit_range: Optional[tuple[int, int]] = None):
+                  emit_range: Optional[tuple[int, int]] = None, median: Optional[np.ndarray] = None):
         """TrackNet stage on device.  Frames from the generator are absolute frames first_frame, first_frame+1, ...
         Returns dict frame_index -> (x, y, vis) for the frames emitted (restricted to emit_range if given)."""
         import itertools
@@ -142,8 +155,8 @@ class BallTracker(Tracker):
         it = iter(frame_generator)
         B = self.batch_size
         pending: list[np.ndarray] = []
-        median = self.median
-        if median is None:  # iterable.py:58-73
+        median = self.median if median is None else median
+        if median is None:  # iterable.py:58-73 (a sharded caller passes the whole-video median instead)
             for f in it:
                 pending.append(f)
                 if len(pending) == self.median_max_sample_num:

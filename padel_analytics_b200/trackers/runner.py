@@ -44,8 +44,13 @@ class FusedPass:
     2 = all trackers concurrent.  The kernels and their inputs are the same in every mode, so are the results."""
 
     def __init__(self, trackers: dict[str, Tracker], frame_hw: tuple[int, int], batch_size: int, total_frames: int,
-                 first_frame: int = 0, emit_range: Optional[tuple[int, int]] = None, streams: Optional[int] = None):
+                 first_frame: int = 0, emit_range: Optional[tuple[int, int]] = None, streams: Optional[int] = None,
+                 raw: bool = False, median=None):
+        """raw=True: the YOLO trackers' entries are the engines' raw per-frame Results (no polygon filter / ByteTrack /
+        result objects) -- what a shard hands to rank 0, where the order-dependent host stages run once over the
+        ordered gather.  median: background for the ball tracker (defaults to BallTracker.median)."""
         self.trackers = trackers
+        self.raw = raw
         self.mode = int(os.environ.get("PADEL_B200_STREAMS", "1")) if streams is None else streams
         self.side = {name: torch.cuda.Stream() for name in trackers}
         self.hw = tuple(frame_hw)
@@ -58,7 +63,7 @@ class FusedPass:
         self.consumed = [None, None]  # per staging slot: event after the device work that read it
         for t in trackers.values():
             if isinstance(t, BallTracker):
-                t.stream_begin(self.hw, total_frames, first_frame, emit_range)
+                t.stream_begin(self.hw, total_frames, first_frame, emit_range, median=median)
 
     def _upload(self, frames, slot: int) -> torch.Tensor:
         if not isinstance(frames, torch.Tensor):
@@ -116,6 +121,8 @@ class FusedPass:
                 out[name] = fin()
             elif fin is None:
                 out[name] = [t.fixed_keypoints_detection] * nfr
+            elif self.raw:
+                out[name] = fin()
             elif isinstance(t, PlayerTracker):
                 out[name] = t.postprocess(fin())
             else:
@@ -186,10 +193,18 @@ class TrackingRunner:
         return sv.get_video_frames_generator(self.video_path, start=self.start + lo, end=self.start + hi)
 
     def run(self, frame_source: Optional[Callable[[int, int], Iterable[np.ndarray]]] = None,
-            total_frames: Optional[int] = None) -> dict[str, float]:
-        """Sequential per-tracker pass (runner.py:185-234).  `frame_source(lo, hi)` yields frames lo..hi-1 (defaults to
-        decoding `video_path`).  Under torch.distributed (world_size > 1) each rank processes its contiguous shard and
-        rank 0 assembles the results; with a single process this is the reference's plain loop."""
+            total_frames: Optional[int] = None, fused: Optional[bool] = None) -> dict[str, float]:
+        """The runner pass (runner.py:185-234).  `frame_source(lo, hi)` yields frames lo..hi-1 (defaults to decoding
+        `video_path`).
+
+        fused (default: on when two or more trackers still need inference): ONE pass over the frames feeds every
+        such tracker from a single decode + upload per batch (`FusedPass`; the reference decodes and uploads once per
+        tracker, runner.py:215-220).  fused=False is the reference's plain loop, one full pass per tracker.
+        Trackers with cached predictions (runner.py:187-191) or a fixed keypoints detection never enter the fused set.
+
+        Under torch.distributed (world_size > 1) each rank processes its contiguous shard, fixed-capacity detection
+        records are all-gathered, and rank 0 runs the order-dependent host stages (polygon filter, ByteTrack ids,
+        InpaintNet, result objects) over the ordered frames."""
         import torch.distributed as dist
 
         src = frame_source or self._frames
@@ -197,44 +212,156 @@ class TrackingRunner:
         dist_on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist_on else (0, 1)
         lo, hi = shard_range(total, rank, world)
-        for name, tracker in self.trackers.items():
-            if len(tracker) != 0:  # cached predictions were loaded (runner.py:187-191)
-                continue
+        todo = {n: t for n, t in self.trackers.items() if len(t) == 0}  # cached predictions: skipped (runner.py:187-191)
+        model = {n: t for n, t in todo.items() if isinstance(t, (PlayerTracker, PlayerKeypointsTracker, BallTracker))
+                 or (isinstance(t, KeypointsTracker) and t.fixed_keypoints_detection is None and t.model is not None)}
+        if fused is None:
+            fused = len(model) >= 2 and torch.cuda.is_available()
+        if fused and model:
+            self._run_fused(model, src, total, lo, hi, rank, world, dist_on)
+            todo = {n: t for n, t in todo.items() if n not in model}
+        for name, tracker in todo.items():
             tracker.to(tracker.DEVICE)
             t0 = timeit.default_timer()
             if isinstance(tracker, BallTracker):
                 flo, fhi = ball_shard_frames(total, lo, hi)
-                part = tracker.track_xyv(src(flo, fhi), total, first_frame=flo, emit_range=(lo, hi))
+                median = self._ball_median(tracker, src, total, rank, dist_on)
+                part = tracker.track_xyv(src(flo, fhi), total, first_frame=flo, emit_range=(lo, hi), median=median)
+                part = _ball_records(part, lo, hi)
             elif isinstance(tracker, (PlayerTracker, PlayerKeypointsTracker, KeypointsTracker)) and \
                     getattr(tracker, "fixed_keypoints_detection", None) is None:
                 part, hw = [], None
                 for sample in sampler(src(lo, hi), tracker.batch_size):
                     hw = sample[0].shape[:2]
                     part += tracker.detect_sample(sample)
-                part = (part, hw)
+                part = (_yolo_records(part, tracker), hw)
             else:
                 part = list(tracker.predict_and_update(src(lo, hi), total_frames=hi - lo).predictions)
             if torch.cuda.is_available():
                 torch.cuda.synchronize()
-            if dist_on:
-                gathered = [None] * world if rank == 0 else None
-                dist.gather_object(part, gathered, dst=0)
-            else:
-                gathered = [part]
-            if rank == 0:
-                self._assemble(tracker, gathered, total)
+            self._gather_and_assemble(tracker, part, total, rank, world, dist_on)
             self.timings[name] = timeit.default_timer() - t0
             tracker.to("cpu")
             if rank == 0:
                 tracker.save_predictions()
         return self.timings
 
+    # ---- fused single pass -------------------------------------------------------------------------------------
+    def _ball_median(self, tracker: BallTracker, src, total: int, rank: int, dist_on: bool):
+        """Background median of the ball tracker.  The reference takes it from the first `median_max_sample_num`
+        frames of the VIDEO (iterable.py:58-73): under sharding rank 0 computes it from those frames (device
+        selection kernel) and broadcasts it, so every shard feeds TrackNet the same background."""
+        import torch.distributed as dist
+
+        if tracker.median is not None:
+            return tracker.median
+        from .ball_tracker import median_background
+
+        med = None
+        if rank == 0:
+            frames = list(src(0, min(total, tracker.median_max_sample_num)))
+            med = median_background(frames)
+        if dist_on:
+            dev = _comm_device()
+            shape = torch.zeros(3, dtype=torch.int64, device=dev)
+            if rank == 0:
+                shape = torch.tensor(med.shape, dtype=torch.int64, device=dev)
+            dist.broadcast(shape, src=0)
+            buf = torch.from_numpy(med).to(dev) if rank == 0 else \
+                torch.empty(tuple(int(v) for v in shape.tolist()), dtype=torch.uint8, device=dev)
+            dist.broadcast(buf, src=0)
+            med = buf.cpu().numpy()
+        return med
+
+    def _run_fused(self, model: dict, src, total: int, lo: int, hi: int, rank: int, world: int, dist_on: bool):
+        """One pass over this rank's frames for every tracker in `model`.  A ball shard needs 7 frames of history and
+        7 of look-ahead (`ball_shard_frames`); the YOLO results of those halo frames are simply dropped."""
+        ball = next((t for t in model.values() if isinstance(t, BallTracker)), None)
+        flo, fhi = ball_shard_frames(total, lo, hi) if ball is not None else (lo, hi)
+        B = min(t.batch_size for t in model.values())  # every engine is sized for its own tracker's batch_size
+        for t in model.values():
+            t.to(t.DEVICE)
+        t0 = timeit.default_timer()
+        median = self._ball_median(ball, src, total, rank, dist_on) if ball is not None else None
+        t_med = timeit.default_timer() - t0
+        it = iter(src(flo, fhi))
+        first = next(it, None)
+        parts = {n: [] for n in model}
+        hw = None
+        if first is not None:
+            hw = tuple(first.shape[:2])
+            single = not dist_on
+            fp = FusedPass(model, hw, B, total_frames=total, first_frame=flo, emit_range=(lo, hi), raw=not single,
+                           median=median)
+            pinned = [torch.empty((B,) + hw + (3,), dtype=torch.uint8).pin_memory() for _ in range(3)]
+
+            def batches():
+                import itertools
+
+                chunk_it = sampler(itertools.chain([first], it), B)
+                for i, chunk in enumerate(chunk_it):
+                    buf = pinned[i % 3]
+                    for j, f in enumerate(chunk):
+                        buf[j].copy_(torch.from_numpy(np.ascontiguousarray(f)))
+                    yield buf[:len(chunk)]
+
+            pos = flo
+            for out in fp.run(batches()):
+                n = None
+                for name, t in model.items():
+                    if isinstance(t, BallTracker):
+                        parts[name].append(out[name])
+                    else:
+                        res = out[name]
+                        n = len(res)
+                        keep = [r for k, r in enumerate(res) if lo <= pos + k < hi]
+                        parts[name] += keep
+                pos += n if n is not None else B
+        torch.cuda.synchronize()
+        t_pass = timeit.default_timer() - t0
+        t1 = timeit.default_timer()
+        for name, t in model.items():
+            if isinstance(t, BallTracker):
+                xyv = {}
+                for d in parts[name]:
+                    xyv.update(d)
+                part = _ball_records(xyv, lo, hi)
+            elif not dist_on:
+                part = parts[name]  # already post-processed objects, in frame order
+            else:
+                part = (_yolo_records(parts[name], t), hw)
+            self._gather_and_assemble(t, part, total, rank, world, dist_on)
+            self.timings[name] = t_pass  # one shared pass: per-tracker times are not separable
+            t.to("cpu")
+            if rank == 0:
+                t.save_predictions()
+        self.timings["_fused_pass"] = t_pass
+        self.timings["_median"] = t_med
+        self.timings["_gather_assemble"] = timeit.default_timer() - t1
+
+    def _gather_and_assemble(self, tracker: Tracker, part, total: int, rank: int, world: int, dist_on: bool) -> None:
+        if not dist_on:
+            if rank == 0:
+                self._assemble(tracker, [part], total)
+            return
+        import torch.distributed as dist
+
+        if isinstance(part, tuple) and isinstance(part[0], YoloRecords):
+            gathered = [(r, part[1]) for r in _all_gather_yolo(part[0], total, rank, world)]
+        elif isinstance(part, BallRecords):
+            gathered = _all_gather_ball(part, total, rank, world)
+        else:  # cached / fixed objects: ragged Python lists, gathered as objects
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(part, gathered, dst=0)
+        if rank == 0:
+            self._assemble(tracker, gathered, total)
+
     @staticmethod
     def _assemble(tracker: Tracker, parts: list, total: int) -> None:
         if isinstance(tracker, BallTracker):
             xyv = {}
             for p in parts:
-                xyv.update(p)
+                xyv.update(p.to_dict() if isinstance(p, BallRecords) else p)
             xyv = tracker.inpaint_xyv(xyv, total)  # whole-trajectory stage: after the shards are merged
             tracker.results.predictions = [
                 Ball(frame=n, xy=(xyv[n][0], xyv[n][1]), visibility=xyv[n][2]) if n in xyv
@@ -242,7 +369,7 @@ class TrackingRunner:
         elif parts and isinstance(parts[0], tuple):
             results, hw = [], None
             for res, h in parts:
-                results += res
+                results += res.to_results(tracker) if isinstance(res, YoloRecords) else res
                 hw = hw or h
             if isinstance(tracker, PlayerTracker):
                 tracker.results.predictions = tracker.postprocess(results)  # ordered => ByteTrack ids are consistent
@@ -250,3 +377,109 @@ class TrackingRunner:
                 tracker.results.predictions = tracker.postprocess(results, hw)
         else:
             tracker.results.predictions = [o for p in parts for o in p]
+
+
+# ---- fixed-capacity records for the gather ---------------------------------------------------------
+class YoloRecords:
+    """Detections of consecutive frames as one dense float32 block (frames, cap, 6 + K*D) + int32 counts: rows are
+    [x1, y1, x2, y2, conf, cls, keypoints...] exactly as the engine's Results hold them."""
+
+    def __init__(self, rows: torch.Tensor, counts: torch.Tensor, kpt_shape):
+        self.rows, self.counts, self.kpt_shape = rows, counts, kpt_shape
+
+    def to_results(self, tracker) -> list:
+        from ..engine.yolo_engine import Boxes, Keypoints, Result
+
+        out = []
+        names = tracker.model.names
+        for i in range(self.rows.shape[0]):
+            r = self.rows[i, : int(self.counts[i])]
+            kp = None
+            if self.kpt_shape:
+                K, D = self.kpt_shape
+                kp = Keypoints(r[:, 6:].reshape(-1, K, D).clone())
+            out.append(Result(Boxes(r[:, :6].clone()), kp, names, None))
+        return out
+
+
+class BallRecords:
+    """(x, y, visibility, present) int32 per frame of a contiguous range starting at `first`."""
+
+    def __init__(self, first: int, data: torch.Tensor):
+        self.first, self.data = first, data
+
+    def to_dict(self) -> dict:
+        return {self.first + i: (int(x), int(y), int(v)) for i, (x, y, v, p) in enumerate(self.data.tolist()) if p}
+
+
+def _yolo_records(results: list, tracker) -> YoloRecords:
+    kpt_shape = tracker.model.kpt_shape
+    rowlen = 6 + (kpt_shape[0] * kpt_shape[1] if kpt_shape else 0)
+    cap = max([len(r.boxes) for r in results], default=0)
+    rows = torch.zeros((len(results), max(cap, 1), rowlen), dtype=torch.float32)
+    counts = torch.zeros((len(results),), dtype=torch.int32)
+    for i, r in enumerate(results):
+        n = len(r.boxes)
+        counts[i] = n
+        if n:
+            rows[i, :n, :6] = r.boxes.data
+            if kpt_shape:
+                rows[i, :n, 6:] = r.keypoints.data.reshape(n, -1)
+    return YoloRecords(rows, counts, kpt_shape)
+
+
+def _ball_records(xyv: dict, lo: int, hi: int) -> BallRecords:
+    data = torch.zeros((hi - lo, 4), dtype=torch.int32)
+    for n, (x, y, v) in xyv.items():
+        if lo <= n < hi:
+            data[n - lo] = torch.tensor([x, y, v, 1], dtype=torch.int32)
+    return BallRecords(lo, data)
+
+
+def _comm_device() -> torch.device:
+    import torch.distributed as dist
+
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def _all_gather_yolo(rec: YoloRecords, total: int, rank: int, world: int) -> list[YoloRecords]:
+    """all_gather of padded fixed-capacity blocks: capacity = the global maximum detections per frame (one MAX
+    all-reduce), frames padded to the longest shard.  Every rank receives every block; rank 0 uses them."""
+    import torch.distributed as dist
+
+    dev = _comm_device()
+    npad = max(shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world))
+    cap = torch.tensor([rec.rows.shape[1]], dtype=torch.int64, device=dev)
+    dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+    cap = int(cap.item())
+    rowlen = rec.rows.shape[2]
+    rows = torch.zeros((npad, cap, rowlen), dtype=torch.float32, device=dev)
+    counts = torch.zeros((npad,), dtype=torch.int32, device=dev)
+    n = rec.rows.shape[0]
+    rows[:n, : rec.rows.shape[1]] = rec.rows.to(dev)
+    counts[:n] = rec.counts.to(dev)
+    all_rows = [torch.empty_like(rows) for _ in range(world)]
+    all_counts = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(all_rows, rows)
+    dist.all_gather(all_counts, counts)
+    out = []
+    for r in range(world):
+        a, b = shard_range(total, r, world)
+        out.append(YoloRecords(all_rows[r][: b - a].cpu(), all_counts[r][: b - a].cpu(), rec.kpt_shape))
+    return out
+
+
+def _all_gather_ball(rec: BallRecords, total: int, rank: int, world: int) -> list[BallRecords]:
+    import torch.distributed as dist
+
+    dev = _comm_device()
+    npad = max(shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world))
+    data = torch.zeros((npad, 4), dtype=torch.int32, device=dev)
+    data[: rec.data.shape[0]] = rec.data.to(dev)
+    parts = [torch.empty_like(data) for _ in range(world)]
+    dist.all_gather(parts, data)
+    out = []
+    for r in range(world):
+        a, b = shard_range(total, r, world)
+        out.append(BallRecords(a, parts[r][: b - a].cpu()))
+    return out

@@ -1,0 +1,206 @@
+"""YOLO detection parity protocol (TEST INFRASTRUCTURE, imports the oracle).
+
+The reference runs its networks in fp32 (TF32 on a GPU); the engine stores activations in fp16 with fp32 accumulation.
+Scores therefore differ by O(1e-2) and a detection whose confidence sits on the threshold, or whose NMS decision
+hinges on an IoU next to `iou_thres` or on the order of two near-equal scores, may legitimately flip.  Instead of
+granting a blanket percentage, the oracle's own candidates are classified by interval reasoning:
+
+    SURE      kept by NMS for every perturbation of the scores by < eps_conf and of the pairwise IoUs by < eps_iou
+    UNCERTAIN kept for some perturbations, dropped for others  ("borderline")
+    NO        never kept
+
+and the bar is:  every SURE candidate has a partner among our detections with IoU >= 0.99 (and every keypoint whose
+visibility is not itself borderline within 0.5 px), and every detection of ours matches a SURE or UNCERTAIN candidate
+(no extras).  The counts of each class are reported so that vacuity is visible.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torchvision
+
+from oracle import yolov8 as OY
+
+SURE, UNCERTAIN, NO = 2, 1, 0
+
+
+@dataclass
+class Candidates:
+    boxes: torch.Tensor  # (n,4) xyxy, network-input pixels, sorted by conf descending
+    conf: torch.Tensor  # (n,)
+    cls: torch.Tensor  # (n,)
+    extra: torch.Tensor  # (n,nk) decoded keypoints (network px, conf)
+    status: torch.Tensor  # (n,) SURE / UNCERTAIN / NO
+    exact_keep: torch.Tensor  # (n,) bool: kept by the oracle's exact NMS (+ max_det)
+    notes: dict = field(default_factory=dict)
+
+
+def classify_candidates(pred_i: torch.Tensor, nc: int, conf_thr: float, iou_thr: float, classes, max_det: int,
+                        eps_conf: float = 0.02, eps_iou: float = 0.03, max_wh: float = 7680.0) -> Candidates:
+    """pred_i: (4+nc+nk, A) decoded head output of ONE image (xywh, class scores, keypoints) as the oracle network
+    returns it.  Follows ultralytics non_max_suppression (oracle/yolov8.py:247-271) with intervals."""
+    p = pred_i.T
+    box = OY.xywh2xyxy(p[:, :4])
+    scores = p[:, 4:4 + nc]
+    conf, j = scores.max(1)
+    amb_cls = torch.zeros_like(conf, dtype=torch.bool)
+    if nc > 1:  # the arg-max class itself may flip when the runner-up is within eps
+        top2 = scores.topk(2, dim=1).values
+        amb_cls = (top2[:, 0] - top2[:, 1]) < eps_conf
+    sel = conf > conf_thr - eps_conf
+    cls_ok = torch.ones_like(sel)
+    if classes is not None:
+        cls_ok = (j[:, None] == torch.tensor(classes)[None]).any(1)
+        sel &= cls_ok | amb_cls
+    idx = sel.nonzero().squeeze(1)
+    order = conf[idx].argsort(descending=True, stable=True)
+    idx = idx[order]
+    b, c, k, ex, amb = box[idx], conf[idx], j[idx].float(), p[idx, 4 + nc:], amb_cls[idx]
+    n = len(idx)
+    iou = torchvision.ops.box_iou(b + k[:, None] * max_wh, b + k[:, None] * max_wh) if n else torch.zeros((0, 0))
+    status = torch.zeros(n, dtype=torch.long)
+    for i in range(n):
+        present_sure = bool(c[i] > conf_thr + eps_conf) and not bool(amb[i])
+        before_sure = c > c[i] + eps_conf  # surely ranked before i (all have a smaller index: status known)
+        before_maybe = (c > c[i] - eps_conf) & ~before_sure
+        before_maybe[i] = False
+        st = status.clone()
+        st[i + 1:] = UNCERTAIN  # not classified yet: may or may not be kept
+        sup_sure = bool((before_sure & (status == SURE) & (iou[:, i] > iou_thr + eps_iou)).any())
+        sup_poss = bool(((before_sure | before_maybe) & (st >= UNCERTAIN) & (iou[:, i] > iou_thr - eps_iou)).any())
+        if sup_sure:
+            status[i] = NO
+        elif present_sure and not sup_poss:
+            status[i] = SURE
+        else:
+            status[i] = UNCERTAIN
+    # max_det: a candidate is surely output only if fewer than max_det possibly-kept candidates can rank before it
+    poss = status >= UNCERTAIN
+    for i in range(n):
+        if status[i] == NO:
+            continue
+        rank_max = int((poss & (c > c[i] - eps_conf)).sum()) - 1
+        rank_min = int(((status == SURE) & (c > c[i] + eps_conf)).sum())
+        if rank_min >= max_det:
+            status[i] = NO
+        elif rank_max >= max_det and status[i] == SURE:
+            status[i] = UNCERTAIN
+    # the oracle's exact answer, for reporting
+    exact = torch.zeros(n, dtype=torch.bool)
+    if n:
+        ok = (c > conf_thr) & (cls_ok[idx] if classes is not None else torch.ones(n, dtype=torch.bool))
+        ii = ok.nonzero().squeeze(1)
+        keep = torchvision.ops.nms(b[ii] + k[ii, None] * max_wh, c[ii], iou_thr)[:max_det]
+        exact[ii[keep]] = True
+    return Candidates(b, c, k, ex, status, exact)
+
+
+def scale_to_image(boxes: torch.Tensor, kpts: torch.Tensor | None, net_hw, img_hw, kpt_shape):
+    """ultralytics scale_boxes / scale_coords (oracle/yolov8.py:274-297)."""
+    b = OY.scale_boxes(net_hw, boxes.clone(), img_hw)
+    k = None
+    if kpt_shape:
+        K, D = kpt_shape
+        k = OY.scale_coords(net_hw, kpts.reshape(-1, K, D).clone(), img_hw)
+    return b, k
+
+
+@dataclass
+class ImageReport:
+    n_sure: int
+    n_uncertain: int
+    n_exact: int
+    n_exact_sure: int
+    n_ours: int
+    sure_unmatched: list  # (conf, best_iou, w, h) of SURE candidates without an IoU >= 0.99 partner
+    extras: list  # (conf, best_iou) of our detections matching no SURE/UNCERTAIN candidate
+    min_iou_sure: float
+    max_conf_err: float
+    max_kpt_px: float
+    n_kpt_checked: int
+
+
+def compare_image(cand: Candidates, ours_boxes: torch.Tensor, ours_conf: torch.Tensor, ours_kpts, net_hw, img_hw,
+                  kpt_shape, frame_scale=(1.0, 1.0), iou_bar: float = 0.99, eps_kconf: float = 0.02) -> ImageReport:
+    """ours_*: the engine's Result for this image (image coordinates).  frame_scale: factor from image px to original
+    frame px per axis (the keypoint bar is in frame pixels; PIL-square paths scale by W/S, H/S)."""
+    cb, ck = scale_to_image(cand.boxes, cand.extra, net_hw, img_hw, kpt_shape)
+    possible = cand.status >= UNCERTAIN
+    sure = cand.status == SURE
+    M = len(ours_boxes)
+    iou = torchvision.ops.box_iou(cb, ours_boxes) if (len(cb) and M) else torch.zeros((len(cb), M))
+    sure_unmatched, min_iou, conf_err, kmax, nk = [], 1.0, 0.0, 0.0, 0
+    fs = torch.tensor(frame_scale, dtype=torch.float32)
+    for i in sure.nonzero().squeeze(1).tolist():
+        best, j = (iou[i].max(0) if M else (torch.tensor(0.0), None))
+        best = float(best)
+        min_iou = min(min_iou, best)
+        if best < iou_bar:
+            w, h = float(cb[i, 2] - cb[i, 0]), float(cb[i, 3] - cb[i, 1])
+            sure_unmatched.append((round(float(cand.conf[i]), 4), round(best, 4), round(w, 1), round(h, 1)))
+            continue
+        j = int(j)
+        conf_err = max(conf_err, abs(float(ours_conf[j]) - float(cand.conf[i])))
+        if kpt_shape and ours_kpts is not None:
+            K, D = kpt_shape
+            ek = ck[i]  # (K,D)
+            gk = ours_kpts[j]
+            if D == 3:
+                stable = (ek[:, 2] - 0.5).abs() > eps_kconf
+                vis = ek[:, 2] >= 0.5
+                exy = torch.where(vis[:, None], ek[:, :2], torch.zeros_like(ek[:, :2]))
+            else:
+                stable = torch.ones(K, dtype=torch.bool)
+                exy = ek[:, :2]
+            d = ((exy - gk[:, :2]) * fs).norm(dim=-1)
+            if stable.any():
+                kmax = max(kmax, float(d[stable].max()))
+                nk += int(stable.sum())
+    extras = []
+    for j in range(M):
+        ok = (iou[possible, j] >= iou_bar).any() if possible.any() else False
+        if not bool(ok):
+            best = float(iou[:, j].max()) if len(cb) else 0.0
+            extras.append((round(float(ours_conf[j]), 4), round(best, 4)))
+    return ImageReport(int(sure.sum()), int((cand.status == UNCERTAIN).sum()), int(cand.exact_keep.sum()),
+                       int((cand.exact_keep & sure).sum()), M, sure_unmatched, extras, min_iou, conf_err, kmax, nk)
+
+
+def oracle_predictions(net, x: torch.Tensor) -> torch.Tensor:
+    """(B, 4+nc+nk, A) decoded oracle head output on the pre-processed batch x."""
+    with torch.no_grad():
+        return net(x)
+
+
+def check_batch(net, x, results, conf, iou, classes, max_det, img_hw, frame_scale=(1.0, 1.0), eps_conf=0.02,
+                eps_iou=0.03, verbose=True, tag=""):
+    """Full protocol for one pre-processed batch `x` (B,3,Hn,Wn) and the engine's `results` (list of Result in image
+    coordinates).  Returns the list of ImageReport; raises AssertionError when the bar is missed."""
+    pred = oracle_predictions(net, x)
+    reports = []
+    for i, r in enumerate(results):
+        cand = classify_candidates(pred[i], net.nc, conf, iou, classes, max_det, eps_conf, eps_iou)
+        kp = r.keypoints.data if r.keypoints is not None else None
+        rep = compare_image(cand, r.boxes.xyxy, r.boxes.conf, kp, tuple(x.shape[2:]), img_hw, net.kpt_shape, frame_scale)
+        reports.append(rep)
+        if verbose:
+            print(f"{tag} img{i}: oracle kept {rep.n_exact} (sure {rep.n_exact_sure}), candidates sure {rep.n_sure} "
+                  f"borderline {rep.n_uncertain}, ours {rep.n_ours}; min IoU on sure {rep.min_iou_sure:.4f}, "
+                  f"max |dconf| {rep.max_conf_err:.4f}, max kpt err {rep.max_kpt_px:.3f} px over {rep.n_kpt_checked}; "
+                  f"sure-unmatched {rep.sure_unmatched[:6]} extras {rep.extras[:6]}")
+    return reports
+
+
+def assert_reports(reports, kind="", min_sure_frac=0.5):
+    tot_sure = sum(r.n_sure for r in reports)
+    tot_exact = sum(r.n_exact for r in reports)
+    assert tot_exact > 0, f"{kind}: vacuous, the oracle found no detections"
+    assert tot_sure >= min_sure_frac * tot_exact, f"{kind}: vacuous, only {tot_sure} sure of {tot_exact} oracle detections"
+    bad = [(i, r.sure_unmatched) for i, r in enumerate(reports) if r.sure_unmatched]
+    assert not bad, f"{kind}: non-borderline oracle detections without an IoU>=0.99 partner: {bad}"
+    ext = [(i, r.extras) for i, r in enumerate(reports) if r.extras]
+    assert not ext, f"{kind}: detections matching no (sure or borderline) oracle candidate: {ext}"
+    kmax = max(r.max_kpt_px for r in reports)
+    assert kmax < 0.5, f"{kind}: keypoint error {kmax:.3f} px >= 0.5 px on a non-borderline keypoint"

@@ -171,6 +171,64 @@ dist.destroy_process_group()
     assert "WORLD2_OK" in r.stdout, r.stdout + r.stderr
 
 
+def _fake_results(frames, kpt_shape, seed=0):
+    """Deterministic ragged per-frame Results (0..5 detections) keyed by absolute frame number."""
+    from padel_analytics_b200.engine.yolo_engine import Boxes, Keypoints, Result
+
+    out = []
+    for n in frames:
+        g = torch.Generator().manual_seed(1000 * seed + n)
+        k = int(torch.randint(0, 6, (1,), generator=g))
+        box = torch.rand((k, 6), generator=g) * 100 + n
+        kp = None
+        if kpt_shape:
+            kp = Keypoints(torch.rand((k,) + tuple(kpt_shape), generator=g) * 50 + n)
+        out.append(Result(Boxes(box), kp, {0: "x"}, None))
+    return out
+
+
+def test_runner_world2_gloo_fixed_capacity_records(tmp_path):
+    """The sharded gather of SURVEY 8(e): ragged per-frame detections -> padded (frames, cap, 6+K*D) blocks + counts,
+    all_gather over gloo, rank 0 rebuilds the frame-ordered Results; ball (x, y, vis) int32 records likewise."""
+    script = tmp_path / "w2.py"
+    script.write_text(f"""
+import sys
+sys.path.insert(0, {str(ROOT)!r}); sys.path.insert(0, {str(ROOT / 'tests')!r})
+import torch, torch.distributed as dist
+from types import SimpleNamespace
+from test_host_cpu import _fake_results
+from padel_analytics_b200.trackers import runner as R
+dist.init_process_group('gloo')
+rank, world, total = dist.get_rank(), dist.get_world_size(), 23
+lo, hi = R.shard_range(total, rank, world)
+for kpt_shape in (None, (13, 3)):
+    trk = SimpleNamespace(model=SimpleNamespace(kpt_shape=kpt_shape, names={{0: 'x'}}))
+    rec = R._yolo_records(_fake_results(range(lo, hi), kpt_shape), trk)
+    parts = R._all_gather_yolo(rec, total, rank, world)
+    got = [r for p in parts for r in p.to_results(trk)]
+    exp = _fake_results(range(total), kpt_shape)
+    assert len(got) == total
+    for g, e in zip(got, exp):
+        assert torch.equal(g.boxes.data, e.boxes.data)
+        if kpt_shape:
+            assert torch.equal(g.keypoints.data, e.keypoints.data)
+xyv = {{n: (n, 2 * n, n % 2) for n in range(lo, hi) if n % 5}}
+ball = R._all_gather_ball(R._ball_records(xyv, lo, hi), total, rank, world)
+merged = {{}}
+for b in ball:
+    merged.update(b.to_dict())
+assert merged == {{n: (n, 2 * n, n % 2) for n in range(total) if n % 5}}, merged
+if rank == 0:
+    print('RECORDS_OK')
+dist.destroy_process_group()
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29519", str(script)], capture_output=True,
+                       text=True, env=env, timeout=240)
+    assert "RECORDS_OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_ball_tracker_inpaint_host_logic_reproduces_reference_golden():
     """BallTracker._inpaint_stage (product host code: mask, sequences, blend, COOR_TH, coordinate ensemble, float32 pixel
     conversion) driven with the CPU oracle network instead of the CUDA kernel must reproduce the golden produced by the
