@@ -87,7 +87,16 @@ def make_tracknet(seed: int = SEEDS["tracknet"], frac_above: float = 1e-2) -> di
     return {"param_dict": {"seq_len": 8, "bg_mode": "concat"}, "model": net.state_dict()}
 
 
-def make_yolo(kind: str, scale: str = "n", seed: int | None = None, cls_mean: float | None = None) -> dict:
+def calib_from_frame(frame_bgr, imgsz: int = 640) -> torch.Tensor:
+    """A natural frame (HWC uint8 BGR) as a calibration input: RGB, letterboxed like the detect path."""
+    from .yolov8 import letterbox
+
+    lb = letterbox(frame_bgr, imgsz, auto=True)[..., ::-1]
+    return torch.from_numpy(lb.transpose(2, 0, 1).copy()).float().unsqueeze(0) / 255.0
+
+
+def make_yolo(kind: str, scale: str = "n", seed: int | None = None, cls_mean: float | None = None,
+              calib: torch.Tensor | None = None) -> dict:
     """kind: 'detect' (nc=80), 'pose13' (nc=1, 13x3 kpts), 'court12' (nc=1, 12x3 kpts).  Last layers are
     standardised on a calibration image so that O(1%) of the anchors exceed the trackers' confidence thresholds
      with varied box sizes; for 'detect' class 0 (person) dominates the other 79."""
@@ -96,8 +105,8 @@ def make_yolo(kind: str, scale: str = "n", seed: int | None = None, cls_mean: fl
     net = YoloV8(scale, nc, kpt).eval()
     _init_convs(net, g, gain=1.6)
     head = net.model[22]
-    with torch.no_grad():
-        feats = net.features(_calib_yolo_input())
+    with torch.no_grad():  # calib: (1,3,H,W) input to standardise on (default: the synthetic scene)
+        feats = net.features(_calib_yolo_input() if calib is None else calib)
     # default: dense detections (parity tests want many candidates); bench.py passes a lower cls_mean so that a
     # frame yields a realistic handful of players
     if cls_mean is None:

@@ -12,9 +12,12 @@ from typing import Iterable, Optional
 import numpy as np
 
 try:  # pragma: no cover - not installed in the build image
+    import types as _types
+
     import supervision as _sv  # type: ignore
 
-    HAVE_SUPERVISION = True
+    # a test harness may have planted a mock under this name: only a real module counts
+    HAVE_SUPERVISION = isinstance(_sv, _types.ModuleType) and isinstance(getattr(_sv, "__version__", None), str)
 except Exception:  # noqa: BLE001
     _sv = None
     HAVE_SUPERVISION = False

@@ -8,6 +8,13 @@ ball_ref.npz  — the reference BallTracker.predict_frames TrackNet stage (ball_
                 it returned, captured by wrapping `predict_modified`.  (predict_frames then dies with KeyError 'Frame',
                 SURVEY App. E q6 — the TrackNet stage has completed by then.)
 tracknet_ref.npz — reference TrackNet forward on one seeded input (models.py:45-74).
+yolo_glue_ref.npz — the reference's OWN PlayerKeypointsTracker.predict_sample / KeypointsTracker.predict_sample /
+                PlayerTracker.predict_sample (players_keypoints_tracker.py:271-322, keypoints_tracker.py:199-262,
+                players_tracker.py:341-380) driven with the oracle YOLO as the `ultralytics.YOLO` stub, on the three
+                rally.mp4 crops under tests/golden/rally/: what the reference's glue (processor, predict arguments,
+                ratio scaling, id mapping, object construction) makes of a given model output.  ultralytics itself
+                stays unpinned (absent); for PlayerTracker the `supervision` names are bound to this repo's sv_compat
+                (supervision is absent too), so only the reference's own lines are pinned there.
 """
 import sys
 import tempfile
@@ -24,6 +31,8 @@ from oracle import ref_harness, weights as OW  # noqa: E402
 from padel_analytics_b200 import synth  # noqa: E402
 
 OUT = Path(__file__).resolve().parent
+sys.path.insert(0, str(OUT.parent))
+from fixtures import court_conf_for_single_detection, glue_ckpt, rally_frames  # noqa: E402
 
 
 def main():
@@ -118,6 +127,8 @@ def main():
         print("inpaint_ref: tracknet vis", int(tv.sum()), "-> inpainted vis", int(sum(b.visibility for b in balls)),
               [b.xy for b in balls][:14])
 
+    yolo_glue_golden()
+
     net = TrackNet(27, 8)
     net.load_state_dict(ck["model"])
     net.eval()
@@ -129,5 +140,62 @@ def main():
     print("tracknet_ref:", y.shape, float(y.mean()))
 
 
+def yolo_glue_golden():
+    """Reference tracker classes (unmodified) + oracle YOLO -> tests/golden/yolo_glue_ref.npz."""
+    import trackers.keypoints_tracker.keypoints_tracker as rkt
+    import trackers.players_keypoints_tracker.players_keypoints_tracker as rpk
+    import trackers.players_tracker.players_tracker as rpt
+    from padel_analytics_b200.trackers import sv_compat
+
+    frames = rally_frames()
+    H, W = frames[0].shape[:2]
+    out = {"H": H, "W": W, "n": len(frames)}
+    with tempfile.TemporaryDirectory() as td:
+        paths = {}
+        for kind in ("detect", "pose13", "court12"):
+            paths[kind] = str(Path(td) / f"{kind}.pt")
+            torch.save(glue_ckpt(kind), paths[kind])
+        # --- PlayerKeypointsTracker (needs >= 3 players per frame, SURVEY App. E q4)
+        pk = rpk.PlayerKeypointsTracker(paths["pose13"], 640, batch_size=len(frames), load_path=None, save_path=None)
+        preds = pk.predict_sample(frames)
+        for i, p in enumerate(preds):
+            arr = np.array([[kp.xy for kp in player.player_keypoints] for player in p.players_keypoints], dtype=np.float64)
+            assert arr.shape[0] >= 3 and arr.shape[1:] == (13, 2), arr.shape
+            out[f"pose_{i}"] = arr
+        out["pose_names"] = np.array([kp.name for kp in preds[0].players_keypoints[0].player_keypoints])
+        # --- KeypointsTracker: exactly one detection per frame (q5) -> per-frame CONF via a subclass attribute
+        net = OW.load_yolo(glue_ckpt("court12"))
+        confs = []
+        for i, f in enumerate(frames):
+            conf = court_conf_for_single_detection(net, f)
+            confs.append(conf)
+            cls = type("CourtOne", (rkt.KeypointsTracker,), {"CONF": conf})
+            kt = cls(paths["court12"], batch_size=1, model_type="yolo")
+            (kp,) = kt.predict_sample([f])
+            ks = sorted(kp.keypoints, key=lambda k: k.id)
+            assert [k.id for k in ks] == list(range(12))
+            out[f"court_{i}"] = np.array([k.xy for k in ks], dtype=np.float64)
+        out["court_conf"] = np.array(confs)
+        # --- PlayerTracker: supervision names bound to sv_compat (Detections.from_ultralytics, PolygonZone, ByteTrack)
+        rpt.sv = sv_compat
+        try:
+            poly = sv_compat.PolygonZone(np.array([[0, 0], [W, 0], [W, H], [0, H]]),
+                                         frame_resolution_wh=(W, H))
+            pt = rpt.PlayerTracker(paths["detect"], poly, batch_size=len(frames))
+            pt.video_info_post_init(sv_compat.VideoInfo(width=W, height=H, fps=25.0, total_frames=len(frames)))
+            preds = pt.predict_sample(frames)
+            for i, p in enumerate(preds):
+                out[f"players_{i}"] = np.array([[*pl.xyxy, pl.confidence, pl.class_id, -1 if pl.id is None else pl.id]
+                                                for pl in p.players], dtype=np.float64).reshape(-1, 7)
+        finally:
+            rpt.sv = sys.modules["supervision"]
+    np.savez_compressed(OUT / "yolo_glue_ref.npz", **out)
+    print("yolo_glue_ref:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if "--yolo-glue-only" in sys.argv:
+        ref_harness.import_reference()
+        yolo_glue_golden()
+    else:
+        main()

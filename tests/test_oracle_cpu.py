@@ -124,3 +124,58 @@ def test_inpaint_stage_matches_reference_golden():
                                  int(g["seq_len"]), (int(g["net_h"]), int(g["net_w"])), batch_size=int(g["B"]))
     assert sum(mask) > 5 and sum(g["vis"].tolist()) < len(mask)  # the mask and the gaps are exercised
     assert out["X"] == g["X"].tolist() and out["Y"] == g["Y"].tolist() and out["Visibility"] == g["V"].tolist()
+
+
+def test_tracker_glue_reproduces_reference_golden():
+    """tests/golden/yolo_glue_ref.npz was produced by the UNMODIFIED reference tracker classes (predict_sample of
+    PlayerKeypointsTracker / KeypointsTracker / PlayerTracker) driving the oracle YOLO on the committed rally.mp4 crops.
+    The product trackers' host glue (processor semantics, predict arguments, ratio scaling, id mapping, result objects)
+    fed with the same oracle results must reproduce it EXACTLY; the GPU tests then only have to show engine == oracle."""
+    import cv2
+    from PIL import Image
+
+    from fixtures import GOLDEN, court_conf_for_single_detection, glue_ckpt, rally_frames
+    from oracle import yolov8 as OY
+    from padel_analytics_b200.trackers import sv_compat as sv
+    from padel_analytics_b200.trackers.keypoints_tracker import KeypointsTracker
+    from padel_analytics_b200.trackers.players_keypoints_tracker import PlayerKeypoints, PlayerKeypointsTracker
+    from padel_analytics_b200.trackers.players_tracker import PlayerTracker
+
+    g = np.load(GOLDEN / "yolo_glue_ref.npz")
+    frames = rally_frames()
+    H, W = frames[0].shape[:2]
+    assert (H, W, len(frames)) == (int(g["H"]), int(g["W"]), int(g["n"]))
+    rgb = [cv2.cvtColor(f, cv2.COLOR_BGR2RGB) for f in frames]
+    pil = [Image.fromarray(f).resize((640, 640)) for f in rgb]
+
+    # pose (players_keypoints_tracker.py:271-322)
+    pk = object.__new__(PlayerKeypointsTracker)  # no CUDA here: skip the engine, keep the class constants
+    pk.train_image_size = 640
+    res = OY.YOLO(OW.load_yolo(glue_ckpt("pose13"))).predict(pil, conf=pk.CONF, iou=pk.IOU, imgsz=640, classes=[0])
+    out = pk.postprocess(res, (H, W))
+    assert list(g["pose_names"]) == PlayerKeypoints.KEYPOINTS_NAMES
+    for i, p in enumerate(out):
+        arr = np.array([[kp.xy for kp in pl.player_keypoints] for pl in p.players_keypoints], dtype=np.float64)
+        assert np.array_equal(arr, g[f"pose_{i}"]), f"pose frame {i}"
+        assert [kp.id for kp in p.players_keypoints[0].player_keypoints] == list(range(13))
+
+    # court (keypoints_tracker.py:199-262), one detection per frame by construction of the golden
+    net = OW.load_yolo(glue_ckpt("court12"))
+    kt = object.__new__(KeypointsTracker)
+    for i, f in enumerate(frames):
+        conf = court_conf_for_single_detection(net, f)
+        assert conf == float(g["court_conf"][i])
+        res = OY.YOLO(net).predict([pil[i]], conf=conf, iou=kt.IOU, imgsz=kt.TRAIN_IMAGE_SIZE, max_det=kt.NUMBER_KEYPOINTS)
+        (kp,) = kt.postprocess(res, (H, W))
+        assert [k.id for k in kp.keypoints] == list(range(12))
+        assert np.array_equal(np.array([k.xy for k in kp.keypoints]), g[f"court_{i}"]), f"court frame {i}"
+
+    # players (players_tracker.py:341-380) with this repo's supervision stand-ins on both sides
+    pt = object.__new__(PlayerTracker)
+    pt.polygon_zone = sv.PolygonZone(np.array([[0, 0], [W, 0], [W, H], [0, H]]), frame_resolution_wh=(W, H))
+    pt.video_info_post_init(sv.VideoInfo(width=W, height=H, fps=25.0, total_frames=len(frames)))
+    res = OY.YOLO(OW.load_yolo(glue_ckpt("detect"))).predict(rgb, conf=pt.CONF, iou=pt.IOU, imgsz=pt.IMGSZ, classes=[0])
+    for i, p in enumerate(pt.postprocess(res)):
+        arr = np.array([[*pl.xyxy, pl.confidence, pl.class_id, -1 if pl.id is None else pl.id] for pl in p.players],
+                       dtype=np.float64).reshape(-1, 7)
+        assert np.array_equal(arr, g[f"players_{i}"]), f"players frame {i}"
