@@ -64,8 +64,10 @@ SIGNATURES = {
     "pb_pil_resize_u8": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _i, _i, _p, _i, _p]),
     "pb_u8_to_f16_nhwc16": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p]),
     "pb_tracknet_pack_windows": (_i, [_p, _i, _i, _p, _i, _i, _i, _p, _p]),
-    "pb_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _i, _p]),
-    "pb_yolo_nms": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p, _p]),
+    "pb_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _i, _i, _i, _i, _f, C.POINTER(C.c_int), _i, _p, _p, _p,
+                             _i, _p]),
+    "pb_yolo_nms_scratch_bytes": (C.c_size_t, [_i, _i]),
+    "pb_yolo_nms": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p, _p, _p]),
     "pb_inpaintnet_forward": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "pb_median_u8": (_i, [_p, _i, C.c_longlong, _p, _i, _p]),
     "pb_tracknet_ensemble": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p]),

@@ -22,14 +22,15 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
 ]
-# bring-up only: PADEL_B200_EXPERIMENTAL=tma_store,staged compiles the experimental epilogues in;
-# the product build defines neither
-_EXP = list(filter(None, os.environ.get("PADEL_B200_EXPERIMENTAL", "").split(",")))
-if _EXP:  # experimental builds never overwrite the product library (load one with PADEL_B200_LIB=<path>)
-    LIB = HERE / "libpadel_b200_exp.so"
-    OBJ = HERE / "build_exp"
-for _x in _EXP:
-    NVCC_FLAGS.append({"tma_store": "-DPB_EXPERIMENTAL_TMA_STORE", "staged": "-DPB_EXPERIMENTAL_STAGED_EPILOGUE"}[_x])
+# Bring-up build (`python -m padel_analytics_b200.build --debug`): the same sources + csrc/debug/*.cu with
+# -DPB_DEBUG_BUILD -> libpadel_b200_debug.so, which adds the pb_debug_* hooks the scripts/exp_*.py experiments use.
+# It never overwrites the product library (whose exported ABI is exactly include/padel_b200.h); load it with
+# PADEL_B200_LIB=padel_analytics_b200/libpadel_b200_debug.so.
+DEBUG_BUILD = "--debug" in sys.argv or os.environ.get("PADEL_B200_DEBUG_BUILD") == "1"
+if DEBUG_BUILD:
+    LIB = HERE / "libpadel_b200_debug.so"
+    OBJ = HERE / "build_debug"
+    NVCC_FLAGS.append("-DPB_DEBUG_BUILD")
 
 
 def _nvcc() -> str:
@@ -49,12 +50,13 @@ def _digest(paths) -> str:
 
 
 def sources():
-    return sorted(CSRC.glob("*.cu"))
+    return sorted(CSRC.glob("*.cu")) + (sorted((CSRC / "debug").glob("*.cu")) if DEBUG_BUILD else [])
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> Path:
     srcs = sources()
-    deps = srcs + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "padel_b200.h"]
+    deps = srcs + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "padel_b200.h",
+                                                                          CSRC / "exports.map"]
     stamp = OBJ / "stamp.txt"
     dig = _digest(deps)
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
@@ -76,7 +78,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static",
+           "-Xlinker", f"--version-script={CSRC / 'exports.map'}"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

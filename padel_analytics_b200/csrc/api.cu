@@ -67,18 +67,6 @@ const char* pb_last_error(void) { return g_error.c_str(); }
 int pb_version(void) { return 100; }
 long long pb_launch_count(void) { return g_launches.load(); }
 
-// bring-up: which experimental code paths this library was compiled with (bit 0: staged stores, bit 1: bulk stores)
-int pb_debug_build_flags(void) {
-  int f = 0;
-#ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE
-  f |= 1;
-#endif
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-  f |= 2;
-#endif
-  return f;
-}
-
 int pb_conv2d(const pb_conv_desc* d, void* stream) {
   ConvPlan plan;
   if (conv_plan_build(d, &plan)) return 1;

@@ -150,17 +150,27 @@ __device__ __forceinline__ bool epilogue_fast_ok(const ConvKParams& kp) {
   return false;
 }
 
-// SiLU on a pair with one reciprocal: 1/(1+ea) = db * r, 1/(1+eb) = da * r, r = 1/(da*db).  The exponent is clamped
-// to 2^60 so the product stays finite; silu(v) for v < -41 is below 1e-16 either way (fp16 zero).
-// Experimental (PADEL_B200_CONV_DEBUG bit 0): 1.5 instead of 2 MUFU operations per value, but measured within noise
-// on the YOLO programs (the epilogue is latency- not MUFU-bound), so the plain form stays the default.
-__device__ __forceinline__ void silu2(float& a, float& b) {
-  const float ea = ex2_approx(fminf(a * -1.4426950408889634f, 60.f));
-  const float eb = ex2_approx(fminf(b * -1.4426950408889634f, 60.f));
-  const float da = 1.f + ea, db = 1.f + eb;
-  const float r = rcp_approx(da * db);
-  a *= db * r;
-  b *= da * r;
+// SiLU on four values with ONE reciprocal: 1/da = db*dc*dd * r, ... with r = 1/(da*db*dc*dd), d = 1 + 2^(-v*log2 e).
+// The fast epilogue of a wide SiLU layer is bound by the XU (MUFU) pipe -- ncu on the pose head conv 64->192 @160^2:
+// sm__inst_executed_pipe_xu_realtime 75 %, every other pipe < 45 % (profiles/r02_ncu_yolo.md) -- and the plain form
+// v / (1 + exp(-v)) costs two MUFU operations per value (EX2 + RCP); this one costs 1.25 plus a few FMULs on the
+// idle FMA pipe, with the same few-ulp fp32 accuracy (no approximation of the function itself).
+// The exponent is clamped to 2^30 so that the product of four stays finite (< 2^121); silu(v) for v < -20.8 is below
+// 2e-8 in magnitude either way, i.e. an fp16 zero / smallest subnormal.
+// PADEL_B200_CONV_DEBUG bit 0 selects the plain two-MUFU form for A/B runs.
+__device__ __forceinline__ void silu4(float& a, float& b, float& c, float& d) {
+  constexpr float kNegLog2e = -1.4426950408889634f;
+  const float da = 1.f + ex2_approx(fminf(a * kNegLog2e, 30.f));
+  const float db = 1.f + ex2_approx(fminf(b * kNegLog2e, 30.f));
+  const float dc = 1.f + ex2_approx(fminf(c * kNegLog2e, 30.f));
+  const float dd = 1.f + ex2_approx(fminf(d * kNegLog2e, 30.f));
+  const float pab = da * db, pcd = dc * dd;
+  const float r = rcp_approx(pab * pcd);
+  const float rab = pcd * r, rcd = pab * r;  // 1 / (da db), 1 / (dc dd)
+  a *= db * rab;
+  b *= da * rab;
+  c *= dd * rcd;
+  d *= dc * rcd;
 }
 
 // Where one thread's 16-channel chunk goes: byte pointer of the pixel (channel 0 of the N tile), byte strides of the
@@ -187,7 +197,7 @@ __device__ __forceinline__ void epi_compute16(int act, bool has_res, bool plain_
       for (int i = 0; i < 16; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) silu2(v[2 * i], v[2 * i + 1]);
+      for (int i = 0; i < 4; ++i) silu4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
   } else if (act == PB_ACT_RELU) {
 #pragma unroll
@@ -257,7 +267,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOu
   uint32_t ra[16], rb[16];
   const int act = kp.act;
   const bool has_res = kp.res != nullptr;
-  const bool plain_silu = (kp.dbg_flags & 1) == 0;
+  const bool plain_silu = (kp.dbg_flags & 1) != 0;
   const int cbytes = eo.mode == PB_OUT_F32_NHWC ? 64 : 32;  // bytes of one 16-channel chunk in the output
   int j = 0, c = 0;
   tmem_ld16(t_addr0, ra);
@@ -291,189 +301,9 @@ __device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOu
 #undef PB_EPI_STAGE
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Staged variant of the fast epilogue (fp16 NHWC / UP2 stores, >= 2 chunks per pixel).
-// Measured with scripts/exp_epi_bench.py: a warp store whose 32 lanes each write 32 bytes of a DIFFERENT 128-byte
-// line (lane = pixel, pixel stride = out_C * 2 bytes) costs ~64 cycles of a per-SM serial resource (~2 cycles per line
-// touched), i.e. 16 B/clk/SM no matter how many warps store -- the limiter of every small-channel layer.  Here each
-// warp transposes groups of up to four chunks (64 channels = one 128-byte line per pixel) through a private 4 KB
-// shared-memory tile (XOR-swizzled, conflict-free both ways) so that four lanes write the four 32-byte pieces of ONE
-// pixel: a store instruction then touches 8 lines instead of 32.
-// RESULT: slower on every layer tried (1x1 32->32 @320^2: 141 -> 399 us; 3x3 64->192 @160^2: 191 -> 241 us), so the
-// limit is not the number of lines per instruction -- more likely bytes moved from registers (16 B/clk/SM).  Kept
-// behind -DPB_EXPERIMENTAL_STAGED_EPILOGUE + PADEL_B200_CONV_DEBUG bit 2 as a documented negative result; the
-// product path uses epilogue_fast.
-// ------------------------------------------------------------------------------------------------------------
-#ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE  // compiling it in costs registers / spills in the product kernels: off
-__device__ __forceinline__ uint32_t epi_swz(int row) { return (uint32_t)(((row & 3) << 1) | ((row >> 2) & 1)); }
-
-__device__ __forceinline__ void epilogue_fast_staged(const ConvKParams& kp, const EpiOut& eo, uint32_t t_addr0, int S,
-                                                     uint32_t sub_cols, int nch, const float* __restrict__ sbias,
-                                                     char* op0, const __half* rp0, size_t sub_out, size_t sub_res,
-                                                     uint32_t valid_mask, char* stage, size_t px_step) {
-  uint32_t ra[16], rb[16];
-  const int act = kp.act;
-  const bool has_res = kp.res != nullptr;
-  const bool plain_silu = (kp.dbg_flags & 1) == 0;
-  const int lane = threadIdx.x & 31, jj = lane & 3, g4 = lane & ~3;
-  char* wrow = stage + lane * 128;
-  const uint32_t wsw = epi_swz(lane);
-  tmem_ld16(t_addr0, ra);
-  for (int j = 0; j < S; ++j) {
-    const bool valid = ((valid_mask >> j) & 1u) != 0;
-    const uint32_t vm = __ballot_sync(0xffffffffu, valid);
-    char* opj = op0 + (size_t)j * sub_out;
-    const __half* rpj = rp0 + (size_t)j * sub_res;
-    const uint32_t t_j = t_addr0 + (uint32_t)j * sub_cols;
-    for (int c0 = 0; c0 < nch; c0 += 4) {
-      const int gsz = nch - c0 < 4 ? nch - c0 : 4;
-      int jn = j, cn0 = c0 + 4;
-      if (cn0 >= nch) {
-        cn0 = 0;
-        ++jn;
-      }
-      const bool more_groups = jn < S;
-      const uint32_t t_next = t_addr0 + (uint32_t)jn * sub_cols + (uint32_t)(cn0 * 16);
-#define PB_EPI_GSTAGE(s, cur, nxt)                                                                       \
-  if (s < gsz) {                                                                                         \
-    const int c = c0 + s;                                                                                \
-    uint4 rv[2] = {};                                                                                    \
-    if (has_res && valid) {                                                                              \
-      const uint4* rp = reinterpret_cast<const uint4*>(rpj + c * 16);                                    \
-      rv[0] = __ldg(rp);                                                                                 \
-      rv[1] = __ldg(rp + 1);                                                                             \
-    }                                                                                                    \
-    tmem_ld_wait16(cur);                                                                                 \
-    bool deferred = false;                                                                               \
-    if (s + 1 < gsz) tmem_ld16(t_j + (uint32_t)((c + 1) * 16), nxt);                                     \
-    else if (more_groups) {                                                                              \
-      if ((s & 1) == 1) tmem_ld16(t_next, nxt); /* nxt == ra: the next group's first buffer */           \
-      else deferred = true;                     /* cur == ra: reload it once this chunk is consumed */    \
-    }                                                                                                    \
-    float v[16];                                                                                         \
-    epi_compute16(act, has_res, plain_silu, cur, sbias + c * 16, rv, v);                                 \
-    if (deferred) tmem_ld16(t_next, cur);                                                                \
-    uint4 pk[2];                                                                                         \
-    __half2* h2 = reinterpret_cast<__half2*>(pk);                                                        \
-    _Pragma("unroll") for (int q = 0; q < 8; ++q) h2[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);    \
-    *reinterpret_cast<uint4*>(wrow + (((uint32_t)(2 * s) ^ wsw) << 4)) = pk[0];                          \
-    *reinterpret_cast<uint4*>(wrow + (((uint32_t)(2 * s + 1) ^ wsw) << 4)) = pk[1];                      \
-  }
-      PB_EPI_GSTAGE(0, ra, rb)
-      PB_EPI_GSTAGE(1, rb, ra)
-      PB_EPI_GSTAGE(2, ra, rb)
-      PB_EPI_GSTAGE(3, rb, ra)
-#undef PB_EPI_GSTAGE
-      __syncwarp();
-      if (jj < gsz) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int r = g4 + k;
-          const uint32_t rsw = epi_swz(r);
-          const char* rrow = stage + r * 128;
-          const uint4 a = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)(2 * jj) ^ rsw) << 4));
-          const uint4 b = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)(2 * jj + 1) ^ rsw) << 4));
-          if ((vm >> r) & 1u) {
-            char* o = opj + (ptrdiff_t)(k - jj) * (ptrdiff_t)px_step + (size_t)((c0 + jj) * 32);
-            st_global_256(o, a, b);
-            if (eo.mode == PB_OUT_F16_NHWC_UP2) {
-              st_global_256(o + eo.dx, a, b);
-              st_global_256(o + eo.dy, a, b);
-              st_global_256(o + eo.dy + eo.dx, a, b);
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
-  }
-}
-#endif  // PB_EXPERIMENTAL_STAGED_EPILOGUE
-
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-// ------------------------------------------------------------------------------------------------------------
-// Bulk-store epilogue (EXPERIMENTAL, compiled out by default; not yet validated on hardware).
-// Each epilogue warp owns 32 pixels of a sub-tile (4 rows x 8 columns).  Per slab of `cb` channels (64 / 32 / 16) it
-// writes the activated fp16 values into a private shared-memory tile [32 pixels][cb] in the TMA swizzle pattern
-// (16-byte unit u of row l goes to u ^ f(l), conflict-free), then one lane issues a single cp.async.bulk.tensor store
-// of the box (cb, 8, 1, 4, 1); the TMA unit clips ragged tiles.  Two tiles per warp, reuse guarded by
-// cp.async.bulk.wait_group.read 1.  Takes the LSU out of the store path.
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t bulk_swz(int l, int cb) {
-  return cb == 64 ? (uint32_t)(l & 7) : (cb == 32 ? (uint32_t)((l >> 1) & 3) : (uint32_t)((l >> 2) & 1));
-}
-
-// `x0`, `y0`, `n`: output coordinates of the warp's first pixel of sub-tile 0 (column of sub-tile j = x0 + 8 j);
-// `ch_base`: first output channel of this N tile in the output tensor, `nch`: its 16-channel chunks.
-__device__ __forceinline__ void epilogue_bulk(const ConvKParams& kp, const CUtensorMap* tmap_out, uint32_t t_addr0, int S,
-                                              uint32_t sub_cols, const float* __restrict__ sbias,
-                                              const __half* rp0, size_t sub_res, uint32_t valid_mask, char* stage,
-                                              int x0, int y0, int n, int ch_base, int nch, uint32_t& toggle) {
-  uint32_t ra[16], rb[16];
-  const int act = kp.act;
-  const bool has_res = kp.res != nullptr;
-  const bool plain_silu = (kp.dbg_flags & 1) == 0;
-  const int lane = threadIdx.x & 31;
-  const int cb = kp.bulk_cb, cpc = cb >> 4;  // chunks per slab
-  const uint32_t sw = bulk_swz(lane, cb);
-  tmem_ld16(t_addr0, ra);
-  for (int j = 0; j < S; ++j) {
-    const bool valid = ((valid_mask >> j) & 1u) != 0;
-    const __half* rpj = rp0 + (size_t)j * sub_res;
-    const uint32_t t_j = t_addr0 + (uint32_t)j * sub_cols;
-    for (int c0 = 0; c0 < nch; c0 += cpc) {
-      char* buf = stage + toggle * 4096;
-      // the store issued two slabs ago read this buffer: wait until it has
-      if (lane == 0) bulk_wait_group_read<1>();
-      __syncwarp();
-      char* wrow = buf + lane * (cb * 2);
-      int jn = j, cn0 = c0 + cpc;
-      if (cn0 >= nch) {
-        cn0 = 0;
-        ++jn;
-      }
-      const bool more_groups = jn < S;
-      const uint32_t t_next = t_addr0 + (uint32_t)jn * sub_cols + (uint32_t)(cn0 * 16);
-#define PB_EPI_BSTAGE(s, cur, nxt)                                                                       \
-  if (s < cpc) {                                                                                         \
-    const int c = c0 + s;                                                                                \
-    uint4 rv[2] = {};                                                                                    \
-    if (has_res && valid) {                                                                              \
-      const uint4* rp = reinterpret_cast<const uint4*>(rpj + c * 16);                                    \
-      rv[0] = __ldg(rp);                                                                                 \
-      rv[1] = __ldg(rp + 1);                                                                             \
-    }                                                                                                    \
-    tmem_ld_wait16(cur);                                                                                 \
-    bool deferred = false;                                                                               \
-    if (s + 1 < cpc) tmem_ld16(t_j + (uint32_t)((c + 1) * 16), nxt);                                     \
-    else if (more_groups) {                                                                              \
-      if ((s & 1) == 1) tmem_ld16(t_next, nxt);                                                          \
-      else deferred = true;                                                                              \
-    }                                                                                                    \
-    float v[16];                                                                                         \
-    epi_compute16(act, has_res, plain_silu, cur, sbias + c * 16, rv, v);                                 \
-    if (deferred) tmem_ld16(t_next, cur);                                                                \
-    uint4 pk[2];                                                                                         \
-    __half2* h2 = reinterpret_cast<__half2*>(pk);                                                        \
-    _Pragma("unroll") for (int q = 0; q < 8; ++q) h2[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);    \
-    *reinterpret_cast<uint4*>(wrow + (((uint32_t)(2 * s) ^ sw) << 4)) = pk[0];                           \
-    *reinterpret_cast<uint4*>(wrow + (((uint32_t)(2 * s + 1) ^ sw) << 4)) = pk[1];                       \
-  }
-      PB_EPI_BSTAGE(0, ra, rb)
-      PB_EPI_BSTAGE(1, rb, ra)
-      PB_EPI_BSTAGE(2, ra, rb)
-      PB_EPI_BSTAGE(3, rb, ra)
-#undef PB_EPI_BSTAGE
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA unit
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_5d(tmap_out, buf, ch_base + c0 * 16, x0 + 8 * j, 0, y0, n);
-        bulk_commit_group();
-      }
-      toggle ^= 1u;
-    }
-  }
-}
-#endif  // PB_EXPERIMENTAL_TMA_STORE
+// Two alternative store paths were built and measured on B200 and then removed (profiles/r02_exp_epilogue.md): a
+// shared-memory transposition so that every store instruction covers full 128-byte lines (slower on every layer), and
+// a TMA bulk-store epilogue (cp.async.bulk.tensor from a swizzled smem tile: 34/34 correctness cases pass, no gain on
+// any program, and merely compiling it in cost the product kernels 20 % through register pressure).
 
 }  // namespace pb

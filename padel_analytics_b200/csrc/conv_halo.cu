@@ -64,9 +64,6 @@ __device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t row_b
 template <bool kPair, int kS, int kSteps>
 __global__ void __launch_bounds__(kConvMaxThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-                 const __grid_constant__ CUtensorMap tmap_out,
-#endif
                  const __grid_constant__ ConvKParams kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -120,9 +117,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (pair) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
-  // PDL: the prologue above touched constant data only; from here on activations are read and written
+  // PDL: the prologue above touched constant data only; from here on activations are read and written.  The weight
+  // producer (warp 6) reads constants only and starts fetching while the previous kernel is still running.
   griddep_launch_dependents();
-  griddep_wait();
+  if (warp != 6) griddep_wait();
 
   if (warp == 0) {
     // ===================== halo producer: one TMA box per (tile, channel block) =====================
@@ -157,13 +155,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncwarp();
   } else if (warp == 6) {
     // ===================== weight producer: one TMA box per (channel block, tap group) =====================
+    // Resident mode (kp.b_resident: the whole filter bank fits next to the halo ring): every box is fetched ONCE per
+    // CTA and reused by all its tiles -- without it a small-channel layer re-reads its weights from L2 for every
+    // tile, as many bytes as the activations themselves.
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
       for (int tile = cta0; tile < kp.total_tiles; tile += cstride) {
         for (int cb = 0; cb < kp.kblocks; ++cb) {
           for (int tg = 0; tg < tap_groups; ++tg) {
-            mbar_wait(&tail->b_empty[st], ph ^ 1);
+            if (!kp.b_resident) mbar_wait(&tail->b_empty[st], ph ^ 1);
             if (pair) {  // each CTA fetches its half of the output channels
               if (crank == 0) mbar_arrive_expect_tx(&tail->b_full[st], 2u * kp.b_tx_bytes);
               tma_load_3d_2sm(b_base + (size_t)st * kp.b_bytes, &tmap_w, &tail->b_full[st], cb * kp.KB,
@@ -178,6 +179,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
         }
+        if (kp.b_resident) break;
       }
     }
     __syncwarp();
@@ -214,7 +216,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint64_t a_desc0 = umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), a_row_bytes, sbo);
           for (int tg = 0; tg < tap_groups; ++tg) {
             const long long tb = dbg ? clock64() : 0;
-            mbar_wait(&tail->b_full[bst], bph);
+            mbar_wait(&tail->b_full[bst], kp.b_resident ? 0u : bph);  // resident: filled once, phase 0 stays complete
             tc_fence_after();
             if (dbg) bwait += clock64() - tb;
             const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(b_base + (size_t)bst * kp.b_bytes), row_bytes);
@@ -237,7 +239,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
               }
             }
-            if (pair) umma_commit_2sm_p(&tail->b_empty[bst], lead); else umma_commit_p(&tail->b_empty[bst], lead);
+            if (!kp.b_resident) {
+              if (pair) umma_commit_2sm_p(&tail->b_empty[bst], lead); else umma_commit_p(&tail->b_empty[bst], lead);
+            }
             if (++bst == kp.b_stages) {
               bst = 0;
               bph ^= 1;
@@ -268,10 +272,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int m = quarter * 32 + lane;
     const int row = m >> 3, col = m & 7;
     const bool fast = epilogue_fast_ok(kp);
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-    uint32_t bulk_toggle = 0;
-    if (kp.bulk_cb != 0 && lane == 0) tma_prefetch_desc(&tmap_out);
-#endif
     int seq = egroup, acc = egroup;  // sequence number / accumulator stage / phase by counters (egroups <= acc_stages)
     uint32_t acc_ph = 0;
     for (int tile = cta0 + egroup * cstride; egroup < kp.egroups && tile < kp.total_tiles;
@@ -302,22 +302,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * kp.acc_cols);
         char* obase = reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)kp.out_coff * esz;
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-        if (kp.bulk_cb != 0)
-          epilogue_bulk(kp, &tmap_out, t0, S, (uint32_t)kp.acc_cols, tail->bias, kp.res + pix0 * kp.res_C + kp.res_coff,
-                        (size_t)8 * kp.res_C, vm,
-                        reinterpret_cast<char*>(smem) + kp.epi_stage_off + (egroup * 4 + quarter) * 8192,
-                        t.tw * 8 * S, t.th * 16 + 4 * quarter, t.n, kp.out_coff, kp.cout_store >> 4, bulk_toggle);
-        else
-#endif
-#ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE
-        if (kp.epi_stage_off != 0 && eo.mode != PB_OUT_F32_NHWC && kp.cout_store >= 32)
-          epilogue_fast_staged(kp, eo, t0, S, (uint32_t)kp.acc_cols, kp.cout_store >> 4, tail->bias, obase,
-                               kp.res + pix0 * kp.res_C + kp.res_coff, sub_out, (size_t)8 * kp.res_C, vm,
-                               reinterpret_cast<char*>(smem) + kp.epi_stage_off + (egroup * 4 + quarter) * 4096,
-                               eo.mode == PB_OUT_F16_NHWC_UP2 ? 2 * pxb : pxb);
-        else
-#endif
           epilogue_fast(kp, eo, t0, S, (uint32_t)kp.acc_cols, (kp.cout_store + 15) >> 4, kp.cout_store, tail->bias,
                         obase, kp.res + pix0 * kp.res_C + kp.res_coff, sub_out, (size_t)8 * kp.res_C, vm);
       } else
@@ -369,9 +353,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         acc_ph ^= 1u;
       }
     }
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-    if (kp.bulk_cb != 0 && lane == 0) bulk_wait_group<0>();  // the last bulk stores must have left shared memory and landed
-#endif
   }
 
   tc_fence_before();
@@ -399,7 +380,6 @@ static void halo_finish_config(ConvPlan* plan) {
   const bool occ2 = !kp.pair && (!eo || atoi(eo) != 0) && need <= 110 * 1024 && set_cols * 2 <= 256 &&
                     kp.total_tiles > num_sms();
   plan->smem_bytes = need;
-  kp.epi_stage_off = 0;
   if (occ2) {
     if (kp.acc_stages * set_cols > 256) kp.acc_stages = 256 / set_cols;
     kp.tmem_cols = 256;
@@ -415,18 +395,6 @@ static void halo_finish_config(ConvPlan* plan) {
     if (kp.pair) {  // total_tiles counts pair tiles: two CTAs each
       const int pairs = kp.total_tiles < num_sms() / 2 ? kp.total_tiles : num_sms() / 2;
       plan->grid = 2 * pairs;
-    }
-  }
-  // store staging (epilogue_fast_staged): 4 KB per epilogue warp behind the tail, when it fits
-  {
-    const bool f16 = kp.out_mode == PB_OUT_F16_NHWC || kp.out_mode == PB_OUT_F16_NHWC_UP2;
-    const size_t tail_end = ((size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes +
-                             sizeof(HaloSmemTail) + 127) & ~(size_t)127;
-    const size_t stage_bytes = (size_t)kp.egroups * 4 * 4096;
-    const size_t limit = occ2 ? 112 * 1024 : 227 * 1024;
-    if (f16 && kp.cout_store >= 32 && !kp.pair && (kp.dbg_flags & 4) != 0 && tail_end + stage_bytes + 1024 <= limit && kStagedEpilogueBuilt) {
-      kp.epi_stage_off = (uint32_t)tail_end;
-      if (plan->smem_bytes < tail_end + stage_bytes + 1024) plan->smem_bytes = tail_end + stage_bytes + 1024;
     }
   }
 }
@@ -464,7 +432,8 @@ int conv_stem_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.b_tx_bytes = 3u * (uint32_t)BN * 32u;
   kp.b_bytes = (kp.b_tx_bytes + 1023u) & ~1023u;
   kp.a_stages = 4;
-  kp.b_stages = 4;
+  kp.b_stages = 1;  // the three filter rows are one small box: resident
+  kp.b_resident = 1;
   kp.acc_cols = acc_cols;
   kp.acc_stages = 512 / (S * acc_cols);
   if (kp.acc_stages > kConvMaxAcc) kp.acc_stages = kConvMaxAcc;
@@ -511,26 +480,44 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   // Choose S (sub-tiles per CTA tile: fewer halo + weight bytes per pixel) first, then G (taps per weight box:
   // fewer TMA operations) as large as shared memory allows.
   const uint32_t tap_bytes = (uint32_t)BN * row_bytes;
+  // Resident filter bank: all nine taps of every channel block (one box per block) stay in shared memory for the
+  // whole kernel when they fit next to two halo buffers; otherwise weight boxes are streamed through a ring.
+  // PADEL_B200_CONV_BRES=0 disables (A/B testing).
+  const uint32_t res_box = (9u * tap_bytes + 1023u) & ~1023u;
+  const size_t res_total = (size_t)kp.kblocks * res_box;
+  bool resident = false;
+  {
+    const char* er = getenv("PADEL_B200_CONV_BRES");
+    resident = (!er || atoi(er) != 0) && kp.kblocks <= kHaloMaxB && res_total <= 120 * 1024;
+  }
   int bestS = 0, best_cols = 0, G = 1;
-  for (int S = 4; S >= 1; S >>= 1) {
-    if (S * acc_cols * 2 > 512) continue;  // keep >= 2 accumulator sets in TMEM
-    const uint32_t halo = 18u * (uint32_t)(8 * S + 2) * row_bytes;
-    const uint32_t a_alloc = (halo + 1023u) & ~1023u;
-    int g_fit = 0;
-    for (int g = 9; g >= 1; g = (g == 9 ? 3 : (g == 3 ? 1 : 0))) {
-      const uint32_t ba = ((uint32_t)g * tap_bytes + 1023u) & ~1023u;
-      const int min_b = g == 9 ? 2 : (g == 3 ? 3 : 4);
-      if ((size_t)2 * a_alloc + (size_t)min_b * ba <= budget) {
-        g_fit = g;
-        break;
+  for (int pass = resident ? 0 : 1; pass < 2 && bestS == 0; ++pass) {
+    resident = resident && pass == 0;
+    for (int S = 4; S >= 1; S >>= 1) {
+      if (S * acc_cols * 2 > 512) continue;  // keep >= 2 accumulator sets in TMEM
+      const uint32_t halo = 18u * (uint32_t)(8 * S + 2) * row_bytes;
+      const uint32_t a_alloc = (halo + 1023u) & ~1023u;
+      int g_fit = 0;
+      if (resident) {
+        if ((size_t)2 * a_alloc + res_total <= budget) g_fit = 9;
+      } else {
+        for (int g = 9; g >= 1; g = (g == 9 ? 3 : (g == 3 ? 1 : 0))) {
+          const uint32_t ba = ((uint32_t)g * tap_bytes + 1023u) & ~1023u;
+          const int min_b = g == 9 ? 2 : (g == 3 ? 3 : 4);
+          if ((size_t)2 * a_alloc + (size_t)min_b * ba <= budget) {
+            g_fit = g;
+            break;
+          }
+        }
       }
-    }
-    if (!g_fit) continue;
-    const int cols = (d->W + 8 * S - 1) / (8 * S) * 8 * S;  // padded width actually computed
-    if (bestS == 0 || cols < best_cols) {
-      bestS = S;
-      best_cols = cols;
-      G = g_fit;
+      if (!g_fit) continue;
+      const int cols = (d->W + 8 * S - 1) / (8 * S) * 8 * S;  // padded width actually computed
+      // resident: prefer the largest S that fits (less halo overlap); streaming: the least padding
+      if (bestS == 0 || (!resident && cols < best_cols)) {
+        bestS = S;
+        best_cols = cols;
+        G = g_fit;
+      }
     }
   }
   const uint32_t b_alloc = ((uint32_t)G * tap_bytes + 1023u) & ~1023u;
@@ -549,7 +536,13 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
     const long pair_tiles = (long)((d->W + 8 * S - 1) / (8 * S)) * ((kp.Ho + 31) / 32) * kp.N;
     const bool want = d->cin >= 128 && d->out_mode == PB_OUT_F16_NHWC && pair_tiles >= 2L * (num_sms() / 2);
     kp.pair = (can && (pm == 1 || (pm == 2 && want))) ? 1 : 0;
+    if (kp.pair && resident) {  // forced pair mode: stream the weights (each CTA holds half of them)
+      resident = false;
+      if (G == 9 && (size_t)2 * (((18u * (uint32_t)(8 * bestS + 2) * row_bytes) + 1023u) & ~1023u) + (size_t)2 * b_alloc > budget)
+        return -1;
+    }
   }
+  kp.b_resident = resident ? 1 : 0;
   kp.hs_S = S;
   kp.hs_P = P;
   kp.hs_G = G;
@@ -570,6 +563,16 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.b_tx_bytes = (uint32_t)G * tap_bytes / (kp.pair ? 2u : 1u);  // per CTA
   kp.b_bytes = b_alloc;
   kp.a_stages = 2;
+  if (resident) {
+    // the filter bank occupies kblocks fixed slots; whatever is left goes to halo buffers (up to kHaloMaxA)
+    kp.b_stages = kp.kblocks;
+    const bool small = (size_t)2 * kp.a_bytes + res_total + sizeof(HaloSmemTail) + 1024 <= 108 * 1024 && S * acc_cols * 2 <= 256;
+    const size_t budget2 = small ? (size_t)108 * 1024 - sizeof(HaloSmemTail) - 1024 : budget;
+    int as = (int)((budget2 - res_total) / kp.a_bytes);
+    if (as > kHaloMaxA) as = kHaloMaxA;
+    if (as > 2 * kp.kblocks + 1) as = 2 * kp.kblocks + 1;
+    kp.a_stages = as < 2 ? 2 : as;
+  } else {
   // light layers: size the rings for half an SM so that two CTAs can be co-resident (see halo_finish_config)
   const int min_b_small = G == 9 ? 2 : (G == 3 ? 3 : 4);
   const bool small = (size_t)2 * kp.a_bytes + (size_t)min_b_small * b_alloc + sizeof(HaloSmemTail) + 1024 <= 108 * 1024 &&
@@ -585,6 +588,7 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   if (bs > 9 * kp.kblocks / G * 2) bs = 9 * kp.kblocks / G * 2;
   if (bs < 2) bs = 2;
   kp.b_stages = bs;
+  }
   kp.acc_cols = acc_cols;
   kp.acc_stages = 512 / (S * acc_cols);
   if (kp.acc_stages > kConvMaxAcc) kp.acc_stages = kConvMaxAcc;
@@ -681,7 +685,8 @@ int conv_halo_s2_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn enco
   kp.b_tx_bytes = 9u * tap_bytes;
   kp.b_bytes = b_alloc;
   kp.a_stages = 2;
-  kp.b_stages = 2;
+  kp.b_stages = 1;  // all nine taps are one box: resident
+  kp.b_resident = 1;
   kp.acc_cols = acc_cols;
   kp.acc_stages = 512 / (S * acc_cols);
   if (kp.acc_stages > kConvMaxAcc) kp.acc_stages = kConvMaxAcc;
@@ -718,41 +723,7 @@ int conv_halo_s2_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn enco
   return 0;
 }
 
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-typedef void (*HaloKernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, ConvKParams);
-
-// Bulk-store epilogue set-up: output tensor map + two 4 KB staging tiles per epilogue warp behind the tail.
-// Enabled by PADEL_B200_CONV_DEBUG bit 3 for plain fp16 NHWC stores of single-CTA layers when the tiles fit.
-int conv_halo_out_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode) {
-  ConvKParams& kp = plan->kp;
-  kp.bulk_cb = 0;
-  if ((kp.dbg_flags & 8) == 0 || d->out_mode != PB_OUT_F16_NHWC || kp.pair || d->head_n != 0 ||
-      (d->cout_store & 15) != 0 || ((d->out_C | d->out_coff) & 7) != 0)
-    return 0;
-  const int cb = d->cout_store % 64 == 0 ? 64 : (d->cout_store % 32 == 0 ? 32 : 16);
-  const size_t tail_end = ((size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes + sizeof(HaloSmemTail) +
-                           4095) & ~(size_t)4095;  // 4 KB aligned: the swizzle pattern is on absolute address bits
-  const size_t stage_bytes = (size_t)kp.egroups * 4 * 8192;
-  const bool occ2 = plan->threads == 224;
-  if (tail_end + stage_bytes + 1024 > (occ2 ? (size_t)112 * 1024 : (size_t)227 * 1024)) return 0;
-  const cuuint64_t C = (cuuint64_t)d->out_C, W = (cuuint64_t)kp.Wo, H = (cuuint64_t)kp.Ho;
-  cuuint64_t dims[5] = {C, W, 1, H, (cuuint64_t)d->N};
-  cuuint64_t strides[4] = {C * 2, W * C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[5] = {(cuuint32_t)cb, 8, 1, 4, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode(&plan->tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, d->out, dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
-                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  PB_CHECK(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(out) failed with %d", (int)r);
-  kp.bulk_cb = cb;
-  kp.epi_stage_off = (uint32_t)tail_end;
-  if (plan->smem_bytes < tail_end + stage_bytes + 1024) plan->smem_bytes = tail_end + stage_bytes + 1024;
-  return 0;
-}
-#else
 typedef void (*HaloKernelFn)(CUtensorMap, CUtensorMap, ConvKParams);
-#endif
 
 template <bool kPair>
 static HaloKernelFn halo_kernel_for(int S, int steps) {
@@ -781,13 +752,8 @@ int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
       configured.push_back(reinterpret_cast<const void*>(fn));
     }
   }
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-  cudaError_t le = launch_pdl(fn, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, kp.pair ? 2 : 1,
-                              plan->tmap_a, plan->tmap_w, plan->tmap_out, plan->kp);
-#else
   cudaError_t le = launch_pdl(fn, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, kp.pair ? 2 : 1,
                               plan->tmap_a, plan->tmap_w, plan->kp);
-#endif
   PB_CHECK(le == cudaSuccess,
            "conv(halo): launch failed: %s (pair %d, grid %d, threads %d, smem %zu, tiles %d, S %d, BN %d, KB %d)",
            cudaGetErrorString(le), kp.pair, plan->grid, plan->threads, plan->smem_bytes, kp.total_tiles, kp.hs_S, kp.BN,

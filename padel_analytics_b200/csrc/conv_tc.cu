@@ -50,9 +50,6 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& kp, int tile
 
 __global__ void __launch_bounds__(kConvMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-               const __grid_constant__ CUtensorMap tmap_out,
-#endif
                const __grid_constant__ ConvKParams kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B alignment is required by the 128B swizzle pattern; align explicitly (the launch adds 1 KB of slack).
@@ -86,9 +83,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
-  // PDL: the prologue above touched constant data only; from here on activations are read and written
+  // PDL: the prologue above touched constant data only; from here on activations are read and written.  The weight
+  // producer (warp 6) reads constants only and starts fetching while the previous kernel is still running.
   griddep_launch_dependents();
-  griddep_wait();
+  if (warp != 6) griddep_wait();
 
   if (warp == 0) {
     // ============================== TMA producer: activations ==============================
@@ -206,12 +204,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int th_i = (p >> kp.tw_log2) & THm;
     const int tn_i = p >> (kp.tw_log2 + kp.th_log2);
     const bool fast = epilogue_fast_ok(kp);
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-    uint32_t bulk_toggle = 0;
-    if (kp.bulk_cb != 0 && lane == 0) tma_prefetch_desc(&tmap_out);
-    const int m0 = quarter * 32;  // the warp's 32 pixels start here inside the (TN x TH x TW) tile
-    const int bx0 = m0 & TWm, by0 = (m0 >> kp.tw_log2) & THm, bn0 = m0 >> (kp.tw_log2 + kp.th_log2);
-#endif
     // per-CTA tile sequence number / accumulator stage / phase advance by counters (egroups <= acc_stages)
     int seq = egroup, acc = egroup;
     uint32_t acc_phase = 0;
@@ -249,22 +241,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           char* obase = reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)(kp.out_coff + tc.nt * kp.BN) * esz;
           const __half* rbase = kp.res + px.pix * kp.res_C + kp.res_coff + tc.nt * kp.BN;
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-          if (kp.bulk_cb != 0)
-            epilogue_bulk(kp, &tmap_out, t_addr, 1, 0u, sb, rbase, 0, px.valid ? 1u : 0u,
-                          reinterpret_cast<char*>(smem) + kp.epi_stage_off + (egroup * 4 + quarter) * 8192,
-                          (tc.tw << kp.tw_log2) + bx0, (tc.th << kp.th_log2) + by0,
-                          tc.tn * (128 >> (kp.tw_log2 + kp.th_log2)) + bn0, kp.out_coff + tc.nt * kp.BN, cn >> 4,
-                          bulk_toggle);
-          else
-#endif
-#ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE
-          if (kp.epi_stage_off != 0 && eo.mode != PB_OUT_F32_NHWC && cn >= 32 && (cn & 15) == 0)
-            epilogue_fast_staged(kp, eo, t_addr, 1, 0u, cn >> 4, sb, obase, rbase, 0, 0, px.valid ? 1u : 0u,
-                                 reinterpret_cast<char*>(smem) + kp.epi_stage_off + (egroup * 4 + quarter) * 4096,
-                                 eo.mode == PB_OUT_F16_NHWC_UP2 ? 2 * pxb : pxb);
-          else
-#endif
             epilogue_fast(kp, eo, t_addr, 1, 0u, (cn + 15) >> 4, cn, sb, obase, rbase, 0, 0, px.valid ? 1u : 0u);
         }
       } else
@@ -304,9 +280,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         acc_phase ^= 1u;
       }
     }
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-    if (kp.bulk_cb != 0 && lane == 0) bulk_wait_group<0>();  // the last bulk stores must have left shared memory and landed
-#endif
   }
 
   tc_fence_before();
@@ -339,8 +312,12 @@ static int ilog2(int v) {
   return l;
 }
 
-static long long* g_conv_dbg = nullptr;  // set through pb_debug_conv_timeline (bring-up only)
+#ifdef PB_DEBUG_BUILD  // libpadel_b200_debug.so only: clock64 role timelines of CTA 0 (scripts/exp_timeline*.py)
+static long long* g_conv_dbg = nullptr;
 extern "C" void pb_debug_conv_timeline(long long* buf) { g_conv_dbg = buf; }
+#else
+static long long* const g_conv_dbg = nullptr;
+#endif
 
 static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
   PB_CHECK(d && plan, "conv: null argument");
@@ -413,12 +390,6 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     kp.dbg_flags = df ? atoi(df) : 0;
   }
   plan->variant = 0;
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-  if (stem) {
-    const int rc = conv_stem_setup(d, plan, encode);
-    return rc == 0 ? conv_halo_out_setup(d, plan, encode) : rc;
-  }
-#endif
   if (stem) return conv_stem_setup(d, plan, encode);
   {
     // halo variant for 3x3/s1 layers: default on for cout <= 192 (the layers the per-tap kernel leaves
@@ -427,9 +398,6 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     const int mode = e ? atoi(e) : 2;
     if (mode == 1 || (mode == 2 && d->cout_pad <= 192)) {
       const int rc = d->stride == 2 ? conv_halo_s2_setup(d, plan, encode) : conv_halo_setup(d, plan, encode);
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-      if (rc == 0) return conv_halo_out_setup(d, plan, encode);
-#endif
       if (rc >= 0) return rc;
     }
   }
@@ -514,49 +482,6 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     plan->threads = conv_threads_for(kp.egroups);
     plan->grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
   }
-  // store staging (epilogue_fast_staged): 4 KB per epilogue warp behind the tail, when it fits
-  kp.epi_stage_off = 0;
-  {
-    const bool f16 = d->out_mode == PB_OUT_F16_NHWC || d->out_mode == PB_OUT_F16_NHWC_UP2;
-    const size_t tail_end = ((size_t)stages * stage_bytes + sizeof(ConvSmemTail) + 127) & ~(size_t)127;
-    const size_t stg = (size_t)kp.egroups * 4 * 4096;
-    const size_t limit = occ2 ? 112 * 1024 : 227 * 1024;
-    if (f16 && kp.BN >= 32 && (kp.dbg_flags & 4) != 0 && tail_end + stg + 1024 <= limit && kStagedEpilogueBuilt) {
-      kp.epi_stage_off = (uint32_t)tail_end;
-      if (plan->smem_bytes < tail_end + stg + 1024) plan->smem_bytes = tail_end + stg + 1024;
-    }
-  }
-
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-  // bulk-store epilogue (PADEL_B200_CONV_DEBUG bit 3): output tensor map whose box is one epilogue warp's 32 pixels
-  kp.bulk_cb = 0;
-  if ((kp.dbg_flags & 8) != 0 && d->out_mode == PB_OUT_F16_NHWC && d->head_n == 0 && (d->cout_store & 15) == 0 &&
-      ((d->out_C | d->out_coff) & 7) == 0 && (kp.n_ntiles == 1 || d->cout_store == d->cout_pad)) {
-    int cb = 64;
-    while (cb > 16 && (kp.BN % cb != 0 || d->cout_store % cb != 0)) cb >>= 1;
-    const size_t tail_end = ((size_t)stages * stage_bytes + sizeof(ConvSmemTail) + 4095) & ~(size_t)4095;
-    const size_t stg = (size_t)kp.egroups * 4 * 8192;
-    if (tail_end + stg + 1024 <= (occ2 ? (size_t)112 * 1024 : (size_t)227 * 1024)) {
-      const int bw = TW < 32 ? TW : 32;
-      const int bh = TH < 32 / bw ? TH : 32 / bw;
-      const int bn = 32 / (bw * bh);
-      const cuuint64_t C = (cuuint64_t)d->out_C, W = (cuuint64_t)kp.Wo, H = (cuuint64_t)kp.Ho;
-      cuuint64_t dims[5] = {C, W, 1, H, (cuuint64_t)d->N};
-      cuuint64_t strides[4] = {C * 2, W * C * 2, W * C * 2, H * W * C * 2};
-      cuuint32_t box[5] = {(cuuint32_t)cb, (cuuint32_t)bw, 1, (cuuint32_t)bh, (cuuint32_t)bn};
-      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-      CUresult r = encode(&plan->tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, d->out, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                   : (cb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
-                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      PB_CHECK(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
-      kp.bulk_cb = cb;
-      kp.epi_stage_off = (uint32_t)tail_end;
-      if (plan->smem_bytes < tail_end + stg + 1024) plan->smem_bytes = tail_end + stg + 1024;
-    }
-  }
-#endif
   const CUtensorMapSwizzle swz = kp.KB == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : kp.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -611,13 +536,8 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   PB_CHECK(attr_err == cudaSuccess, "conv: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-  PB_CUDA(launch_pdl(conv_tc_kernel, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, 1, plan->tmap_a,
-                     plan->tmap_w, plan->tmap_out, plan->kp));
-#else
   PB_CUDA(launch_pdl(conv_tc_kernel, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, 1, plan->tmap_a,
                      plan->tmap_w, plan->kp));
-#endif
   count_launch();
   return 0;
 }

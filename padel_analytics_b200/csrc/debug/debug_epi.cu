@@ -1,11 +1,11 @@
 // Bring-up experiment (not part of the product ABI): what does one 16-channel epilogue chunk cost per warp, and how
 // does it scale with the number of epilogue warps?  Each warp repeats `iters` times: tcgen05.ld 16 columns -> (bias
 // + activation) -> fp16 pack -> one 32-byte store per lane (pixel stride 128 bytes), in selectable parts.
-//   parts bit 0: tcgen05.ld + wait     bit 1: bias (smem) + pack + store     bit 2: SiLU     bit 3: paired-rcp SiLU
+//   parts bit 0: tcgen05.ld + wait     bit 1: bias (smem) + pack + store     bit 2: SiLU     bit 3: one-reciprocal-per-four SiLU (silu4)
 //   bit 4: issue the next tcgen05.ld before processing the current chunk (software pipeline)
-#include "conv_common.cuh"
-#include "internal.h"
-#include "ptx.cuh"
+#include "../conv_common.cuh"
+#include "../internal.h"
+#include "../ptx.cuh"
 
 namespace pb {
 
@@ -54,7 +54,7 @@ debug_epi_kernel(long long* __restrict__ cycles, __half* __restrict__ out, int p
     }                                                                                            \
     if (silu) {                                                                                  \
       if (pairs) {                                                                               \
-        _Pragma("unroll") for (int i = 0; i < 8; ++i) silu2(v[2 * i], v[2 * i + 1]);             \
+        _Pragma("unroll") for (int i = 0; i < 4; ++i) silu4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);             \
       } else {                                                                                   \
         _Pragma("unroll") for (int i = 0; i < 16; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-v[i])); \
       }                                                                                          \

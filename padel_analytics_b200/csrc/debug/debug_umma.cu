@@ -1,8 +1,8 @@
 // Bring-up experiment (not part of the product ABI): how does tcgen05.mma address a K-major SWIZZLE_128B operand
 // whose start is NOT 1024-byte aligned (shifted by whole 128-byte rows) and whose 8-row groups are not 1024 bytes
 // apart?  Result decides whether conv taps can be served from one shared halo tile (see DESIGN.md "next").
-#include "internal.h"
-#include "ptx.cuh"
+#include "../internal.h"
+#include "../ptx.cuh"
 
 namespace pb {
 

@@ -89,11 +89,6 @@ inline int conv_pick_egroups(int acc_stages) {
   return want < 1 ? 1 : want;
 }
 constexpr int kConvMaxCout = 1024;
-#ifdef PB_EXPERIMENTAL_STAGED_EPILOGUE
-constexpr bool kStagedEpilogueBuilt = true;
-#else
-constexpr bool kStagedEpilogueBuilt = false;
-#endif
 
 // Division by a launch-time constant as multiply-high + shift (dividend < 2^31): the per-tile coordinate decode of the
 // persistent kernels would otherwise spend ~25 instructions per runtime `/` or `%` in every warp, every tile.
@@ -142,17 +137,14 @@ struct ConvKParams {
   const float* head_b;
   int head_n;
   float* head_out;
+  int b_resident;  // halo variant: 1 = every weight box is fetched once per CTA and stays in shared memory
   int hs_S, hs_P, hs_G, a_stages, b_stages;  // halo variant: sub-tiles, halo pitch (px), taps per weight box, rings
   uint32_t halo_bytes;
   uint32_t hs_a_row_bytes;  // bytes of one halo row in shared memory (KB*2; 2*KB*2 for the stride-2 pixel-pair rows)
   int hs_ntaps, hs_sbo_rows, hs_x0, hs_y0, hs_tile_h;  // taps served from the halo, 8-row group stride (rows), box origin offsets
   int hs_tap_off[9];                                   // smem row offset of each tap's first pixel
   int hs_tap_desc[9];                                  // the same in 16-byte descriptor units (offset * row_bytes / 16)
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-  int bulk_cb;             // channels per bulk-store slab (64 / 32 / 16), 0 = direct stores
-#endif
-  uint32_t epi_stage_off;  // byte offset (from the aligned smem base) of the per-warp 4 KB store-staging tiles; 0 = off
-  int dbg_flags;   // PADEL_B200_CONV_DEBUG: bit0 = paired-reciprocal SiLU, bit1 = no fast epilogue, bit2 = staged (transposed) stores, bit3 = bulk (TMA) stores
+  int dbg_flags;   // PADEL_B200_CONV_DEBUG: bit0 = plain two-MUFU SiLU (default: one reciprocal per four values), bit1 = no fast epilogue
   long long* dbg;  // optional timeline buffer (CTA 0, first 64 tiles): [role 0..2][64][4] clock64 stamps
 };
 
@@ -161,9 +153,6 @@ struct ConvPlan {
   ConvKParams kp;
   CUtensorMap tmap_a;
   CUtensorMap tmap_w;
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-  CUtensorMap tmap_out;  // (out_C, Wo, 1, Ho, N) fp16 output view, box = one epilogue warp's 32 pixels x kp.bulk_cb channels
-#endif
   int grid;
   int threads;
   size_t smem_bytes;
@@ -176,9 +165,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);  // -1: not applicable
 int conv_stem_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);
 int conv_halo_s2_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);  // -1: not applicable
-#ifdef PB_EXPERIMENTAL_TMA_STORE
-int conv_halo_out_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);  // bulk-store epilogue (halo kernel)
-#endif
 int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream);
 int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan);
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);

@@ -84,26 +84,6 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-// TMA stores (shared -> global, bulk async-group completion).  Not used by the product kernels yet: wrappers for the
-// planned bulk-store epilogue (DESIGN.md 3.1 "Next" -- the per-lane 32-byte stores are the measured epilogue limit).
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3,
-                                             int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
-          reinterpret_cast<uint64_t>(m)),
-      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int kPending>
-__device__ __forceinline__ void bulk_wait_group() {  // the stores themselves have completed
-  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
-}
-template <int kPending>
-__device__ __forceinline__ void bulk_wait_group_read() {  // smem of all but the newest kPending groups may be reused
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
-}
-
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, UMMA issue, commit, TMEM loads
 // ----------------------------------------------------------------------------------------------

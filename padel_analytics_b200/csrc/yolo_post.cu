@@ -12,7 +12,9 @@ constexpr int kMaxLevels = 4;
 struct DecodeParams {
   const float* feat[kMaxLevels];
   int h[kMaxLevels], w[kMaxLevels], stride[kMaxLevels], start[kMaxLevels + 1];
-  int nlevels, B, fC, nc, nk, kdim, class_filter, cap, rowlen, cls_off, kpt_off;
+  int nlevels, B, fC, nc, nk, kdim, cap, rowlen, cls_off, kpt_off;
+  int filter;                      // 1: keep only classes whose bit is set in class_mask
+  unsigned long long class_mask[4];  // classes 0..255
   float conf;
 };
 
@@ -44,7 +46,7 @@ __global__ void yolo_decode_kernel(DecodeParams p, float* __restrict__ cand, int
     }
     const float score = sigmoidf_precise(best);
     if (!(score > p.conf)) continue;
-    if (p.class_filter >= 0 && bj != p.class_filter) continue;
+    if (p.filter && !((p.class_mask[(bj >> 6) & 3] >> (bj & 63)) & 1ull)) continue;
     // DFL: softmax over 16 bins, expectation with arange(16)
     float dist[4];
 #pragma unroll
@@ -90,21 +92,30 @@ __global__ void yolo_decode_kernel(DecodeParams p, float* __restrict__ cand, int
   }
 }
 
-// One block per image: bitonic sort of (conf desc, anchor asc) keys in shared memory, then greedy NMS.
-// Dynamic smem: keys u64[P] | slot u32[P] | boxes float4[P] | suppressed u8[P], P = pow2 >= min(count, cap).
+// One block per image: bitonic sort of (conf desc, anchor asc) keys, then greedy NMS.
+// Working set per candidate: key u64 | box float4 | slot u32 | suppressed u8.  Images with at most kNmsSmemCap
+// candidates (every realistic frame) keep it in shared memory; beyond that -- ultralytics runs NMS on up to
+// max_nms = 30000 candidates -- the same code runs on a global scratch area (L2 resident), P = pow2 >= cap entries.
+constexpr int kNmsSmemCap = 4096;
 __global__ void __launch_bounds__(1024)
 yolo_nms_kernel(const float* __restrict__ cand, const int* __restrict__ cand_anchor,
                 const int* __restrict__ cand_count, int cap, int P, int rowlen, float iou_thr, int max_det,
-                float* __restrict__ out, int* __restrict__ out_count) {
+                float* __restrict__ out, int* __restrict__ out_count, uint8_t* __restrict__ scratch) {
   extern __shared__ __align__(16) uint8_t nms_smem[];
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(nms_smem);
-  float4* boxes = reinterpret_cast<float4*>(keys + P);
-  unsigned* slots = reinterpret_cast<unsigned*>(boxes + P);
-  uint8_t* supp = reinterpret_cast<uint8_t*>(slots + P);
   __shared__ int kept_n;
   const int b = blockIdx.x;
   int n = cand_count[b];
   if (n > cap) n = cap;
+  uint8_t* base = nms_smem;
+  int Pl = kNmsSmemCap < P ? kNmsSmemCap : P;
+  if (n > kNmsSmemCap) {  // block-uniform
+    base = scratch + (size_t)b * P * 32;
+    Pl = P;
+  }
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base);
+  float4* boxes = reinterpret_cast<float4*>(keys + Pl);
+  unsigned* slots = reinterpret_cast<unsigned*>(boxes + Pl);
+  uint8_t* supp = reinterpret_cast<uint8_t*>(slots + Pl);
   const float* cb = cand + (size_t)b * cap * rowlen;
   const int* ab = cand_anchor + (size_t)b * cap;
   int Pe = 1;  // sort only the power of two covering this image's candidates
@@ -184,7 +195,8 @@ using namespace pb;
 extern "C" {
 
 int pb_yolo_decode(const pb_yolo_level* levels, int nlevels, int B, int fC, int nc, int nk, int kdim, int cls_off,
-                   int kpt_off, float conf, int class_filter, float* cand, int* cand_anchor, int* cand_count, int cap, void* stream) {
+                   int kpt_off, float conf, const int* classes, int n_classes, float* cand, int* cand_anchor,
+                   int* cand_count, int cap, void* stream) {
   PB_CHECK(levels && cand && cand_anchor && cand_count, "yolo_decode: null pointer");
   PB_CHECK(nlevels >= 1 && nlevels <= kMaxLevels, "yolo_decode: 1..%d levels", kMaxLevels);
   PB_CHECK(nc >= 1 && fC >= 64 + nc + nk, "yolo_decode: feature width %d < 64+nc+nk", fC);
@@ -194,7 +206,14 @@ int pb_yolo_decode(const pb_yolo_level* levels, int nlevels, int B, int fC, int 
   PB_CHECK(kdim == 0 ? nk == 0 : nk % kdim == 0, "yolo_decode: nk not a multiple of kdim");
   DecodeParams p;
   p.nlevels = nlevels; p.B = B; p.fC = fC; p.nc = nc; p.nk = nk; p.kdim = kdim;
-  p.class_filter = class_filter; p.cap = cap; p.rowlen = 6 + nk; p.conf = conf;
+  p.cap = cap; p.rowlen = 6 + nk; p.conf = conf;
+  p.filter = classes != nullptr ? 1 : 0;
+  for (int i = 0; i < 4; ++i) p.class_mask[i] = 0ull;
+  PB_CHECK(classes == nullptr || nc <= 256, "yolo_decode: a class filter supports nc <= 256");
+  for (int i = 0; classes != nullptr && i < n_classes; ++i) {
+    PB_CHECK(classes[i] >= 0 && classes[i] < 256, "yolo_decode: class %d out of range", classes[i]);
+    p.class_mask[classes[i] >> 6] |= 1ull << (classes[i] & 63);
+  }
   p.cls_off = cls_off; p.kpt_off = kpt_off;
   p.start[0] = 0;
   for (int l = 0; l < nlevels; ++l) {
@@ -212,20 +231,24 @@ int pb_yolo_decode(const pb_yolo_level* levels, int nlevels, int B, int fC, int 
   return 0;
 }
 
+size_t pb_yolo_nms_scratch_bytes(int B, int cap) {
+  if (cap <= kNmsSmemCap) return 0;
+  size_t P = 1;
+  while (P < (size_t)cap) P <<= 1;
+  return (size_t)B * P * 32;
+}
+
 int pb_yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count, int B, int cap, int rowlen,
-                float iou, int max_det, float* out, int* out_count, void* stream) {
+                float iou, int max_det, float* out, int* out_count, void* scratch, void* stream) {
   PB_CHECK(cand && cand_anchor && cand_count && out && out_count, "yolo_nms: null pointer");
   int P = 1;
   while (P < cap) P <<= 1;
-  PB_CHECK(P <= 8192, "yolo_nms: candidate capacity %d > 8192", cap);
-  const size_t smem = (size_t)P * (8 + 16 + 4 + 1);
-  static size_t configured = 0;
-  if (smem > configured) {
-    PB_CUDA(cudaFuncSetAttribute(yolo_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  yolo_nms_kernel<<<B, 1024, smem, static_cast<cudaStream_t>(stream)>>>(cand, cand_anchor, cand_count, cap, P,
-                                                                        rowlen, iou, max_det, out, out_count);
+  PB_CHECK(P <= 32768, "yolo_nms: candidate capacity %d > 32768 (ultralytics max_nms is 30000)", cap);
+  PB_CHECK(cap <= kNmsSmemCap || scratch != nullptr, "yolo_nms: cap %d > %d needs a scratch buffer", cap, kNmsSmemCap);
+  const size_t smem = (size_t)(P < kNmsSmemCap ? P : kNmsSmemCap) * (8 + 16 + 4 + 1);
+  PB_CUDA(cudaFuncSetAttribute(yolo_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  yolo_nms_kernel<<<B, 1024, smem, static_cast<cudaStream_t>(stream)>>>(
+      cand, cand_anchor, cand_count, cap, P, rowlen, iou, max_det, out, out_count, static_cast<uint8_t*>(scratch));
   PB_CUDA(cudaGetLastError());
   count_launch();
   return 0;

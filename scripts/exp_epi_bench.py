@@ -1,5 +1,6 @@
 """Cost of one 16-channel epilogue chunk per warp vs number of epilogue warps and enabled parts (csrc/debug_epi.cu)."""
-import ctypes as C, sys
+import ctypes as C, os, sys
+os.environ.setdefault("PADEL_B200_LIB", "padel_analytics_b200/libpadel_b200_debug.so")  # python -m padel_analytics_b200.build --debug
 import torch
 sys.path.insert(0, ".")
 from padel_analytics_b200 import _lib as L

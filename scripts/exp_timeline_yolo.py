@@ -1,5 +1,6 @@
 """clock64 timeline (CTA 0, first tiles) of the large-spatial / few-channel YOLO-pose layers (HBM-bound ones)."""
-import ctypes as C, sys
+import ctypes as C, os, sys
+os.environ.setdefault("PADEL_B200_LIB", "padel_analytics_b200/libpadel_b200_debug.so")  # python -m padel_analytics_b200.build --debug
 import torch
 sys.path.insert(0, ".")
 from padel_analytics_b200 import _lib as L

@@ -1,5 +1,6 @@
 """Micro-benchmark: cycles per tcgen05.mma (M=128, K=16) with A from shared memory vs A staged through TMEM."""
-import ctypes as C, sys
+import ctypes as C, os, sys
+os.environ.setdefault("PADEL_B200_LIB", "padel_analytics_b200/libpadel_b200_debug.so")  # python -m padel_analytics_b200.build --debug
 import torch
 sys.path.insert(0, ".")
 from padel_analytics_b200 import _lib as L

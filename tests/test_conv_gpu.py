@@ -196,17 +196,3 @@ def test_halo_conv_cta_pair_mode(case, monkeypatch):
     monkeypatch.setenv("PADEL_B200_CONV_PAIR", "1")
     bad, mx = run_case(**case)
     assert bad == 0.0, f"pair-mode kernel: {bad*100:.3f}% elements out of tolerance (max err {mx})"
-
-
-@pytest.mark.parametrize("case", CASES + HALO_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
-def test_experimental_bulk_store_epilogue(case, monkeypatch):
-    """Bulk (TMA) store epilogue: only when the library was built with PADEL_B200_EXPERIMENTAL=tma_store."""
-    import ctypes
-
-    lib = L.lib()
-    lib.pb_debug_build_flags.restype = ctypes.c_int
-    if not (lib.pb_debug_build_flags() & 2):
-        pytest.skip("library built without PB_EXPERIMENTAL_TMA_STORE")
-    monkeypatch.setenv("PADEL_B200_CONV_DEBUG", "8")
-    bad, mx = run_case(**case)
-    assert bad == 0.0, f"bulk-store epilogue: {bad*100:.3f}% elements out of tolerance (max err {mx})"

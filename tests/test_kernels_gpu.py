@@ -158,8 +158,12 @@ def test_ccl_bbox_matches_cv2():
         assert tuple(got[i]) == exp, f"mask {i}: got {tuple(got[i])} expected {exp}"
 
 
-@pytest.mark.parametrize("nc,kpt", [(80, None), (1, (13, 3)), (1, (12, 3)), (1, (13, 2))])
-def test_decode_nms_matches_oracle(nc, kpt):
+@pytest.mark.parametrize("nc,kpt,classes,dense", [(80, None, [0], False), (1, (13, 3), None, False),
+                                                  (1, (12, 3), None, False), (1, (13, 2), None, False),
+                                                  (80, None, [0, 3, 17], False),  # class LIST filter (predict(classes=[...]))
+                                                  (80, None, None, False),
+                                                  (1, (13, 3), None, True)])  # > 4096 candidates: global-scratch NMS path
+def test_decode_nms_matches_oracle(nc, kpt, classes, dense):
     torch.manual_seed(nc + (kpt[0] if kpt else 0))
     B, shapes = 3, [(48, 80), (24, 40), (12, 20)]
     nk = kpt[0] * kpt[1] if kpt else 0
@@ -168,7 +172,7 @@ def test_decode_nms_matches_oracle(nc, kpt):
     for (h, w) in shapes:
         r = torch.randn(B, fC, h, w)
         r[:, :64] *= 2.0
-        r[:, 64:64 + nc] = r[:, 64:64 + nc] * 1.5 - (4.0 if nc > 1 else 2.0)
+        r[:, 64:64 + nc] = r[:, 64:64 + nc] * 1.5 - (4.0 if nc > 1 else 2.0) + (6.0 if dense else 0.0)
         raws.append(r)
     head = OY.PoseHead(nc, kpt, (64, 128, 256)) if kpt else OY.DetectHead(nc, (64, 128, 256))
     if kpt:
@@ -184,25 +188,29 @@ def test_decode_nms_matches_oracle(nc, kpt):
     else:
         pred, _, _ = head.decode_boxes(raws)
     conf, iou, max_det = 0.5, 0.7, 300
-    classes = [0] if nc > 1 else None
     exp = OY.non_max_suppression(pred, conf, iou, classes, max_det, nc)
 
     feats = [r.permute(0, 2, 3, 1).contiguous().to(DEV) for r in raws]
     lv = (L.YoloLevel * 3)()
     for l, (f, (h, w), s) in enumerate(zip(feats, shapes, (8, 16, 32))):
         lv[l].feat, lv[l].h, lv[l].w, lv[l].stride = f.data_ptr(), h, w, s
-    cap, rowlen = 4096, 6 + nk
+    cap, rowlen = sum(h * w for h, w in shapes), 6 + nk  # every anchor (5040 here), as the engine sizes it
     cand = torch.zeros((B, cap, rowlen), device=DEV)
     anchor = torch.zeros((B, cap), dtype=torch.int32, device=DEV)
     count = torch.zeros((B,), dtype=torch.int32, device=DEV)
-    L.check(L.lib().pb_yolo_decode(lv, 3, B, fC, nc, nk, kpt[1] if kpt else 0, 64, 64 + nc, conf, 0 if nc > 1 else -1,
+    carr = (C.c_int * len(classes))(*classes) if classes is not None else None
+    L.check(L.lib().pb_yolo_decode(lv, 3, B, fC, nc, nk, kpt[1] if kpt else 0, 64, 64 + nc, conf, carr,
+                                   len(classes) if classes is not None else 0,
                                    cand.data_ptr(), anchor.data_ptr(), count.data_ptr(), cap, L.stream_ptr()))
     out = torch.zeros((B, max_det, rowlen), device=DEV)
     ocnt = torch.zeros((B,), dtype=torch.int32, device=DEV)
+    scratch = torch.empty((max(16, L.lib().pb_yolo_nms_scratch_bytes(B, cap)),), dtype=torch.uint8, device=DEV)
     L.check(L.lib().pb_yolo_nms(cand.data_ptr(), anchor.data_ptr(), count.data_ptr(), B, cap, rowlen, iou, max_det,
-                                out.data_ptr(), ocnt.data_ptr(), L.stream_ptr()))
+                                out.data_ptr(), ocnt.data_ptr(), scratch.data_ptr(), L.stream_ptr()))
     torch.cuda.synchronize()
     assert int(count.max()) <= cap
+    if dense:
+        assert int(count.min()) > 4096, "dense case must exercise the global-scratch path"
     for b in range(B):
         e = exp[b]
         n = int(ocnt[b])
@@ -210,3 +218,71 @@ def test_decode_nms_matches_oracle(nc, kpt):
         assert n > 3, "test is vacuous"
         g = out[b, :n].cpu()
         assert torch.allclose(g, e, rtol=1e-4, atol=2e-3), f"image {b}: max diff {(g-e).abs().max()}"
+
+
+@pytest.mark.parametrize("T", [1, 2, 7, 8, 255, 300, 401])
+def test_median_kernel_matches_numpy(T):
+    """pb_median_u8 == np.median(frames_rgb, 0).astype('uint8') (iterable.py:58-81), odd and even counts, counter
+    spill past 255 frames, constant / bimodal columns, BGR -> RGB output order."""
+    rng = np.random.default_rng(T)
+    H, W = 36, 52
+    fr = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
+    fr[:, 0, 0] = 255
+    fr[:, 0, 1] = 0
+    fr[: T // 2, 0, 2] = 255
+    fr[T // 2:, 0, 2] = 0
+    fr[:, 1] = (fr[:, 1] // 64) * 64  # few distinct values: many ties
+    ref = np.median(fr[..., ::-1], 0).astype("uint8")  # the reference converts BGR -> RGB first
+    src = torch.from_numpy(fr).to(DEV)
+    out = torch.zeros((H, W, 3), dtype=torch.uint8, device=DEV)
+    L.check(L.lib().pb_median_u8(src.data_ptr(), T, H * W * 3, out.data_ptr(), 1, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
+    out2 = torch.zeros((H, W, 3), dtype=torch.uint8, device=DEV)
+    L.check(L.lib().pb_median_u8(src.data_ptr(), T, H * W * 3, out2.data_ptr(), 0, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(out2.cpu().numpy(), np.median(fr, 0).astype("uint8"))
+
+
+def test_median_background_full_frames():
+    """trackers.ball_tracker.median_background on 1080p frames (list of BGR arrays) == the reference's np.median."""
+    from padel_analytics_b200 import synth
+    from padel_analytics_b200.trackers.ball_tracker import median_background
+
+    fr = [f.numpy() for f in synth.make_frames(12, 1080, 1920, start=40)]
+    ref = np.median(np.array([cv2.cvtColor(f, cv2.COLOR_BGR2RGB) for f in fr]), 0).astype("uint8")
+    assert np.array_equal(median_background(fr), ref)
+    assert np.array_equal(median_background(fr[:11]), np.median(np.array([f[..., ::-1] for f in fr[:11]]), 0).astype("uint8"))
+
+
+def test_resamplers_bit_exact_on_natural_frames():
+    """LetterBox and the Pillow resize on real video content (the committed rally.mp4 crops + a 720p frame)."""
+    from fixtures import GOLDEN, rally_frames
+
+    frames = rally_frames() + [cv2.imread(str(GOLDEN / "rally" / "rally_f00_720p.jpg"))]
+    for f in frames:
+        Hs, Ws = f.shape[:2]
+        fr = np.ascontiguousarray(f[None])
+        g = resample.letterbox_geometry(Hs, Ws, 640)
+        xo, xc = resample.cv2_linear_tables(Ws, g["rw"])
+        yo, yc = resample.cv2_linear_tables(Hs, g["rh"])
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+        src, xo, xc, yo, yc = t(fr), t(xo), t(xc), t(yo), t(yc)
+        dst = torch.zeros((1, g["Hn"], g["Wn"], 16), dtype=torch.float16, device=DEV)
+        L.check(L.lib().pb_letterbox_u8_f16(src.data_ptr(), 1, Hs, Ws, dst.data_ptr(), g["Hn"], g["Wn"], g["rh"], g["rw"],
+                                            g["top"], g["left"], xo.data_ptr(), xc.data_ptr(), yo.data_ptr(),
+                                            yc.data_ptr(), 2, 1, 0, 0, L.stream_ptr()))
+        ref = OY.letterbox(f, 640, auto=True)[..., ::-1]
+        exp = (torch.from_numpy(np.ascontiguousarray(ref)).float() * np.float32(1.0 / 255.0)).half()
+        assert torch.equal(dst[0, ..., :3].cpu(), exp)
+        for Wo, Ho in ((512, 288), (640, 640)):
+            bh, kh, ksh = resample.pil_bicubic_tables(Ws, Wo)
+            bv, kv, ksv = resample.pil_bicubic_tables(Hs, Ho)
+            bh, kh, bv, kv = t(bh), t(kh), t(bv), t(kv)
+            tmp = torch.zeros((1, Hs, Wo, 3), dtype=torch.uint8, device=DEV)
+            out = torch.zeros((1, Ho, Wo, 3), dtype=torch.uint8, device=DEV)
+            L.check(L.lib().pb_pil_resize_u8(src.data_ptr(), 1, Hs, Ws, tmp.data_ptr(), out.data_ptr(), Ho, Wo,
+                                             bh.data_ptr(), kh.data_ptr(), ksh, bv.data_ptr(), kv.data_ptr(), ksv, 1,
+                                             None, 0, L.stream_ptr()))
+            refp = np.array(Image.fromarray(cv2.cvtColor(f, cv2.COLOR_BGR2RGB)).resize((Wo, Ho)))
+            assert np.array_equal(out[0].cpu().numpy(), refp)

@@ -34,9 +34,21 @@ def test_ball_tracker_predict_frames_matches_oracle_and_shards():
     bt.video_info_post_init(_vi(T))
     balls = bt.predict_and_update(iter(fr), total_frames=T).predictions
     assert len(balls) == T and [b.frame for b in balls] == list(range(T))
-    same = sum(1 for n, b in enumerate(balls) if (b.xy[0], b.xy[1], b.visibility) == (ora["x"][n], ora["y"][n], ora["vis"][n]))
-    print("ball tracker identical frames", same, "/", T)
-    assert same >= int(0.8 * T)
+    # a frame is threshold-stable when the oracle's own answer does not move if 0.5 is shifted by +-eps (eps > the
+    # measured heat-map error): on every such frame the tracker's (x, y, visibility) must be IDENTICAL
+    eps, scaler = 0.03, (W / 512, H / 288)
+    stable = same = 0
+    for n, b in enumerate(balls):
+        ref = (ora["x"][n], ora["y"][n], ora["vis"][n])
+        alts = [tuple(v[0] for v in OT.predict_from_ensemble(ora["ens"][n:n + 1], scaler, threshold=t))
+                for t in (0.5 - eps, 0.5 + eps)]
+        got = (b.xy[0], b.xy[1], b.visibility)
+        if all(a == ref for a in alts):
+            stable += 1
+            assert got == ref, f"frame {n}: got {got} oracle {ref}"
+        same += int(got == ref)
+    print(f"ball tracker: identical on {same}/{T} frames; {stable} threshold-stable frames, all identical")
+    assert stable >= 3, "vacuous: no stable frames"
     json.dumps([b.serialize() for b in balls])
     # sharded execution (3 contiguous shards, run back to back on this GPU) == unsharded, frame for frame
     full = {n: (b.xy[0], b.xy[1], b.visibility) for n, b in enumerate(balls)}
@@ -67,51 +79,155 @@ def test_yolo_trackers_api_and_parity():
         res = t.predict_and_update(iter(fr)).predictions
         assert len(res) == T  # 2+2+1 batches, last partial
         json.dumps([o.serialize() for o in res])
-    # players: boxes (before ByteTrack) vs oracle through the reference's processing (players_tracker.py:346-359)
-    yolo = OY.YOLO(OW.load_yolo(cks["detect"]))
-    exp = yolo.predict([cv2.cvtColor(f, cv2.COLOR_BGR2RGB) for f in fr[:B]], conf=0.5, iou=0.7, imgsz=640, classes=[0])
-    got = pt.detect_sample(fr[:B])
-    import torchvision
+    import parity
 
-    for e, g in zip(exp, got):
-        iou = torchvision.ops.box_iou(e.boxes.xyxy, g.boxes.xyxy)
-        frac = (iou.max(1).values >= 0.99).float().mean().item()
-        print("players: oracle", len(e.boxes), "ours", len(g.boxes), "matched", frac)
-        assert frac >= 0.9
+    # players: boxes (before ByteTrack) vs oracle through the reference's processing (players_tracker.py:346-359),
+    # borderline-exclusion protocol: every non-borderline oracle box needs an IoU >= 0.99 partner, no extras
+    net = OW.load_yolo(cks["detect"])
+    yolo = OY.YOLO(net)
+    yolo.predict([cv2.cvtColor(f, cv2.COLOR_BGR2RGB) for f in fr[:B]], conf=0.5, iou=0.7, imgsz=640, classes=[0])
+    got = pt.detect_sample(fr[:B])
+    reps = parity.check_batch(net, yolo.last_preprocessed, got, 0.5, 0.7, [0], 300, (H, W), tag="[players tracker]")
+    parity.assert_reports(reps, "players tracker", min_sure_frac=0.2)
     assert all(p.id is not None for p in pt.results.predictions[0])
     # court: the tracker returns 12 keypoints with reference ids (keypoints_tracker.py:214-227)
     k0 = kt.results.predictions[0]
     if len(k0):
         assert sorted(k.id for k in k0) == list(range(12))
-    # pose: coordinates are scaled back to frame pixels (players_keypoints_tracker.py:276-318)
-    yolo = OY.YOLO(OW.load_yolo(cks["pose13"]))
+    # pose: tracker output (frame pixels, players_keypoints_tracker.py:276-318) vs the oracle's non-borderline players
+    net = OW.load_yolo(cks["pose13"])
+    yolo = OY.YOLO(net)
     sample = [Image.fromarray(cv2.cvtColor(f, cv2.COLOR_BGR2RGB)).resize((1280, 1280)) for f in fr[:1]]
-    e = yolo.predict(sample, conf=0.25, iou=0.7, imgsz=1280, classes=[0])[0]
+    yolo.predict(sample, conf=0.25, iou=0.7, imgsz=1280, classes=[0])
+    cand = parity.classify_candidates(parity.oracle_predictions(net, yolo.last_preprocessed)[0], 1, 0.25, 0.7, [0], 300)
+    _, ck = parity.scale_to_image(cand.boxes, cand.extra, (1280, 1280), (1280, 1280), (13, 3))
     g = pk.results.predictions[0]
-    assert abs(len(g) - len(e.boxes)) <= max(3, len(e.boxes) // 20)
-    # match our players to the oracle's by nearest head keypoint... compare on exact index where both agree
-    ex = e.keypoints.xy.numpy() * np.array([W / 1280, H / 1280], dtype=np.float32)
-    gx = np.array([[kp.xy for kp in player] for player in g], dtype=np.float32)
-    d = np.linalg.norm(ex[:, None] - gx[None], axis=-1).max(-1)  # (Ne, Ng) worst keypoint distance
-    close = (d.min(1) < 0.5).mean()
-    print("pose: players with all 13 keypoints within 0.5 px of an oracle player:", close)
-    assert close >= 0.85
+    gx = np.array([[kp.xy for kp in player] for player in g], dtype=np.float64).reshape(-1, 13, 2)
+    ratio = np.array([W / 1280, H / 1280])
+    nsure = 0
+    for i in (cand.status == parity.SURE).nonzero().squeeze(1).tolist():
+        ek = ck[i].numpy().astype(np.float64)
+        stable = np.abs(ek[:, 2] - 0.5) > 0.02  # keypoints whose visibility cut (conf < 0.5 -> (0, 0)) is not borderline
+        exy = np.where(ek[:, 2:3] >= 0.5, ek[:, :2], 0.0) * ratio
+        d = np.linalg.norm(gx - exy[None], axis=-1)  # (players, 13) frame px
+        best = d[:, stable].max(1).min() if len(gx) and stable.any() else 0.0
+        assert best < 0.5, f"sure oracle player {i}: nearest tracker player is {best:.3f} px off on a stable keypoint"
+        nsure += 1
+    print("pose tracker: non-borderline oracle players all matched within 0.5 px:", nsure, "of", int(cand.exact_keep.sum()))
+    assert nsure >= 3, "vacuous"
 
 
-def test_runner_all_four_synthetic():
-    T, B = 12, 4
-    fr = [f.numpy() for f in synth.make_frames(T, H, W)]
-    med = synth.make_median(H, W).numpy()
+def _four_trackers(B, med=None, **ball_kw):
     poly = sv.PolygonZone(np.array([[0, 0], [W - 1, 0], [W - 1, H - 1], [0, H - 1]]), frame_resolution_wh=(W, H))
-    trackers = [PlayerTracker(OW.make_yolo("detect"), poly, batch_size=B),
-                PlayerKeypointsTracker(OW.make_yolo("pose13"), 1280, batch_size=B, load_path=None, save_path=None),
-                KeypointsTracker(OW.make_yolo("court12"), batch_size=B, model_type="yolo"),
-                BallTracker(OW.make_tracknet(), None, batch_size=B, median=med)]
-    run = TrackingRunner(trackers, video_info=_vi(T))
-    timings = run.run(frame_source=lambda lo, hi: iter(fr[lo:hi]), total_frames=T)
-    assert set(timings) == {"players_tracker", "players_keypoints_tracker", "keypoints_tracker", "ball_tracker"}
-    for t in trackers:
+    return [PlayerTracker(OW.make_yolo("detect"), poly, batch_size=B),
+            PlayerKeypointsTracker(OW.make_yolo("pose13", cls_mean=-5.5), 1280, batch_size=B, load_path=None,
+                                   save_path=None),
+            KeypointsTracker(OW.make_yolo("court12"), batch_size=B, model_type="yolo"),
+            BallTracker(OW.make_tracknet(), None, batch_size=B, median=med, **ball_kw)]
+
+
+def _dump(trackers):
+    return {str(t): json.dumps([o.serialize() for o in t.results.predictions]) for t in trackers}
+
+
+def test_runner_fused_default_equals_sequential_reference_loop():
+    """TrackingRunner.run() -- the reference's entry point (runner.py:175-236) -- takes the fused single pass by
+    default (one decode + upload per batch for all four trackers); its results must be identical, object for object,
+    to the reference-style loop of one full pass per tracker (fused=False)."""
+    T, B = 21, 4
+    fr = [f.numpy() for f in synth.make_frames(T, H, W, start=7)]
+    med = synth.make_median(H, W).numpy()
+    src = lambda lo, hi: iter(fr[lo:hi])
+    seq = _four_trackers(B, med)
+    t_seq = TrackingRunner(seq, video_info=_vi(T)).run(frame_source=src, total_frames=T, fused=False)
+    fus = _four_trackers(B, med)
+    run = TrackingRunner(fus, video_info=_vi(T))
+    t_fus = run.run(frame_source=src, total_frames=T)
+    names = {"players_tracker", "players_keypoints_tracker", "keypoints_tracker", "ball_tracker"}
+    assert set(t_seq) == names and names <= set(t_fus) and "_fused_pass" in t_fus
+    for t in fus + seq:
         assert len(t.results) == T
+    a, b = _dump(seq), _dump(fus)
+    for k in names:
+        assert a[k] == b[k], k
+    assert any(len(p) for p in fus[0].results.predictions), "vacuous: no players"
+    # a second run() finds the trackers full and does nothing (cached predictions, runner.py:187-191)
+    assert run.run(frame_source=src, total_frames=T) == run.timings
+
+
+def test_runner_computes_the_background_median_on_device_when_none_is_given():
+    """BallTracker(median=None): the runner derives the median from the first median_max_sample_num frames of the
+    video (iterable.py:58-73) with the selection kernel; same result as handing np.median's output in."""
+    T, B = 20, 4
+    fr = [f.numpy() for f in synth.make_frames(T, H, W, start=3)]
+    src = lambda lo, hi: iter(fr[lo:hi])
+    M = 9
+    ref_med = np.median(np.array([f[..., ::-1] for f in fr[:M]]), 0).astype("uint8")
+    outs = []
+    for med, kw in ((ref_med, {}), (None, {"median_max_sample_num": M})):
+        tr = _four_trackers(B, med, **kw)[2:]  # court + ball: enough to take the fused path
+        TrackingRunner(tr, video_info=_vi(T)).run(frame_source=src, total_frames=T)
+        outs.append(_dump(tr)["ball_tracker"])
+    assert outs[0] == outs[1]
+    # and a later run with a different median at the same resolution must not reuse the cached background
+    bt = BallTracker(OW.make_tracknet(), None, batch_size=B, median=ref_med)
+    bt.video_info_post_init(_vi(T))
+    a = bt.track_xyv(iter(fr), T)
+    other = 255 - ref_med
+    bt.median = other
+    b = bt.track_xyv(iter(fr), T)
+    bt2 = BallTracker(OW.make_tracknet(), None, batch_size=B, median=other)
+    bt2.video_info_post_init(_vi(T))
+    assert b == bt2.track_xyv(iter(fr), T)
+    bt.median = ref_med
+    assert bt.track_xyv(iter(fr), T) == a
+
+
+def test_runner_sharded_over_nccl_equals_unsharded(tmp_path):
+    """World-size-2 NCCL run of TrackingRunner.run (contiguous shards, ball halo, broadcast median, fixed-capacity
+    all_gather, rank-0 ByteTrack/objects) == the single-process run.  Needs two GPUs (`gpurun --gpus 2`)."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = Path(__file__).resolve().parents[1]
+    script = tmp_path / "nccl2.py"
+    script.write_text(f"""
+import sys, json, os
+sys.path.insert(0, {str(root)!r}); sys.path.insert(0, {str(root / 'tests')!r})
+import numpy as np, torch, torch.distributed as dist
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+from padel_analytics_b200 import synth
+from padel_analytics_b200.trackers import TrackingRunner
+from test_trackers_gpu import _four_trackers, _dump, _vi, H, W
+T, B = 37, 4
+fr = [f.numpy() for f in synth.make_frames(T, H, W, start=7)]
+tr = _four_trackers(B, None, median_max_sample_num=11)
+run = TrackingRunner(tr, video_info=_vi(T))
+t = run.run(frame_source=lambda lo, hi: iter(fr[lo:hi]), total_frames=T)
+if dist.get_rank() == 0:
+    open({str(tmp_path / 'sharded.json')!r}, "w").write(json.dumps(_dump(tr)))
+    print("NCCL2_DONE", {{k: round(v, 3) for k, v in t.items()}})
+dist.destroy_process_group()
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True,
+                       text=True, env=env, timeout=900)
+    assert "NCCL2_DONE" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    print(r.stdout[-400:])
+    T, B = 37, 4
+    fr = [f.numpy() for f in synth.make_frames(T, H, W, start=7)]
+    tr = _four_trackers(B, None, median_max_sample_num=11)
+    TrackingRunner(tr, video_info=_vi(T)).run(frame_source=lambda lo, hi: iter(fr[lo:hi]), total_frames=T)
+    sharded = json.loads((tmp_path / "sharded.json").read_text())
+    single = _dump(tr)
+    for k in single:
+        assert sharded[k] == single[k], k
 
 
 def test_fused_pass_equals_per_tracker_passes():
