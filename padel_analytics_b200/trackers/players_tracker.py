@@ -49,7 +49,8 @@ class Player:
     @classmethod
     def from_json(cls, x: dict):
         det = sv.Detections(xyxy=np.array([x["xyxy"]]), confidence=np.array([x["confidence"]]),
-                            tracker_id=np.array([x["id"]]), class_id=np.array([x["class_id"]]))
+                            tracker_id=None if x.get("id") is None else np.array([x["id"]]),
+                            class_id=np.array([x["class_id"]]))
         return cls(detection=det, projection=x.get("projection"))
 
     def serialize(self) -> dict:

@@ -1,8 +1,9 @@
 """Minimal local stand-ins for the `supervision` objects the reference trackers touch (supervision is a third-party
 dependency of the reference, requirements.txt:8, absent from this image).  If the real package is importable it is
 used instead.  Call sites mirrored: /root/reference/trackers/players_tracker/players_tracker.py:311,363-369,333 ;
-main.py:64,108-119 ; runner.py:52,215-220.  ByteTrack ids are UNPINNED: this is a simplified
-IoU tracker with ByteTrack's thresholds, not a bit-exact port.
+main.py:64,108-119 ; runner.py:52,215-220.  ByteTrack follows the published algorithm (Kalman xyah filter, two-stage
+association, unconfirmed-track handling, duplicate pruning) but could not be checked against supervision's own code:
+track ids stay UNPINNED.
 """
 from __future__ import annotations
 
@@ -130,8 +131,11 @@ class PolygonZone:
 
 
 def _iou_matrix(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Pairwise IoU of xyxy boxes (supervision box_iou_batch)."""
+    a = np.asarray(a, dtype=np.float64).reshape(-1, 4)
+    b = np.asarray(b, dtype=np.float64).reshape(-1, 4)
     if len(a) == 0 or len(b) == 0:
-        return np.zeros((len(a), len(b)), np.float32)
+        return np.zeros((len(a), len(b)), np.float64)
     x1 = np.maximum(a[:, None, 0], b[None, :, 0])
     y1 = np.maximum(a[:, None, 1], b[None, :, 1])
     x2 = np.minimum(a[:, None, 2], b[None, :, 2])
@@ -139,80 +143,273 @@ def _iou_matrix(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     inter = np.clip(x2 - x1, 0, None) * np.clip(y2 - y1, 0, None)
     aa = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
     ab = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
-    return inter / (aa[:, None] + ab[None, :] - inter + 1e-9)
+    union = aa[:, None] + ab[None, :] - inter
+    return np.where(union > 0, inter / np.where(union > 0, union, 1.0), 0.0)
+
+
+# ---- ByteTrack (Zhang et al., ECCV 2022) as packaged by supervision: restated from the published algorithm ---------
+# Kalman filter: the 8-state (x, y, aspect, height + velocities) constant-velocity filter of DeepSORT / ByteTrack.
+class _KalmanXYAH:
+    W_POS, W_VEL = 1.0 / 20, 1.0 / 160
+
+    def __init__(self):
+        self.F = np.eye(8)
+        for i in range(4):
+            self.F[i, 4 + i] = 1.0
+        self.H = np.eye(4, 8)
+
+    def initiate(self, m):
+        mean = np.r_[m, np.zeros(4)]
+        h = m[3]
+        std = [2 * self.W_POS * h, 2 * self.W_POS * h, 1e-2, 2 * self.W_POS * h,
+               10 * self.W_VEL * h, 10 * self.W_VEL * h, 1e-5, 10 * self.W_VEL * h]
+        return mean, np.diag(np.square(std))
+
+    def predict(self, mean, cov):
+        h = mean[3]
+        std = [self.W_POS * h, self.W_POS * h, 1e-2, self.W_POS * h, self.W_VEL * h, self.W_VEL * h, 1e-5, self.W_VEL * h]
+        return self.F @ mean, self.F @ cov @ self.F.T + np.diag(np.square(std))
+
+    def update(self, mean, cov, m):
+        h = mean[3]
+        std = [self.W_POS * h, self.W_POS * h, 1e-1, self.W_POS * h]
+        pm = self.H @ mean
+        S = self.H @ cov @ self.H.T + np.diag(np.square(std))
+        import scipy.linalg
+
+        chol = scipy.linalg.cho_factor(S, lower=True, check_finite=False)
+        K = scipy.linalg.cho_solve(chol, (cov @ self.H.T).T, check_finite=False).T
+        return mean + (m - pm) @ K.T, cov - K @ S @ K.T
+
+
+_NEW, _TRACKED, _LOST, _REMOVED = 0, 1, 2, 3
+
+
+class _STrack:
+    def __init__(self, tlbr, score, class_id, det_index):
+        tlbr = np.asarray(tlbr, dtype=np.float64)
+        self._tlwh = np.r_[tlbr[:2], tlbr[2:] - tlbr[:2]]
+        self.score, self.class_id, self.det_index = float(score), class_id, det_index
+        self.mean = self.cov = None
+        self.is_activated = False
+        self.state = _NEW
+        self.track_id = 0
+        self.frame_id = self.start_frame = 0
+        self.tracklet_len = 0
+
+    @property
+    def tlwh(self):
+        if self.mean is None:
+            return self._tlwh.copy()
+        r = self.mean[:4].copy()
+        r[2] *= r[3]
+        r[:2] -= r[2:] / 2
+        return r
+
+    @property
+    def tlbr(self):
+        r = self.tlwh
+        r[2:] += r[:2]
+        return r
+
+    @staticmethod
+    def xyah(tlwh):
+        r = np.asarray(tlwh, dtype=np.float64).copy()
+        r[:2] += r[2:] / 2
+        r[2] /= r[3]
+        return r
+
+    def activate(self, kf, frame_id, new_id):
+        self.kf = kf
+        self.track_id = new_id
+        self.mean, self.cov = kf.initiate(self.xyah(self._tlwh))
+        self.tracklet_len = 0
+        self.state = _TRACKED
+        if frame_id == 1:
+            self.is_activated = True
+        self.frame_id = self.start_frame = frame_id
+
+    def re_activate(self, det, frame_id):
+        self.mean, self.cov = self.kf.update(self.mean, self.cov, self.xyah(det.tlwh))
+        self.tracklet_len = 0
+        self.state = _TRACKED
+        self.is_activated = True
+        self.frame_id = frame_id
+        self.score = det.score
+
+    def update(self, det, frame_id):
+        self.frame_id = frame_id
+        self.tracklet_len += 1
+        self.mean, self.cov = self.kf.update(self.mean, self.cov, self.xyah(det.tlwh))
+        self.state = _TRACKED
+        self.is_activated = True
+        self.score = det.score
+
+
+def _linear_assignment(cost: np.ndarray, thresh: float):
+    if cost.size == 0:
+        return [], list(range(cost.shape[0])), list(range(cost.shape[1]))
+    from scipy.optimize import linear_sum_assignment
+
+    c = cost.copy()
+    c[c > thresh] = thresh + 1e-4
+    rows, cols = linear_sum_assignment(c)
+    matches = [(int(r), int(q)) for r, q in zip(rows, cols) if c[r, q] <= thresh]
+    mr, mc = {r for r, _ in matches}, {q for _, q in matches}
+    return matches, [i for i in range(cost.shape[0]) if i not in mr], [j for j in range(cost.shape[1]) if j not in mc]
+
+
+def _iou_distance(a, b):
+    return 1.0 - _iou_matrix([t.tlbr for t in a], [t.tlbr for t in b]) if (a and b) else \
+        np.zeros((len(a), len(b)), np.float64)
+
+
+def _fuse_score(cost, dets):
+    if cost.size == 0:
+        return cost
+    return 1.0 - (1.0 - cost) * np.array([d.score for d in dets])[None, :]
+
+
+def _joint(a, b):
+    seen, out = set(), []
+    for t in list(a) + list(b):
+        if t.track_id not in seen:
+            seen.add(t.track_id)
+            out.append(t)
+    return out
+
+
+def _sub(a, b):
+    drop = {t.track_id for t in b}
+    return [t for t in a if t.track_id not in drop]
 
 
 class ByteTrack:
-    """Simplified ByteTrack: high/low score split, IoU association (Hungarian), constant-velocity box prediction,
-    lost-track buffer, ids from a global counter starting at 1.  Stateful and sequential (runs on rank 0)."""
+    """ByteTrack with supervision's constructor and `update_with_detections` contract (players_tracker.py:311,367-369).
+
+    Per frame: detections are split into high (score > track_activation_threshold) and low (0.1 < score <= threshold)
+    sets; all tracked + lost tracks are Kalman-predicted; 1st association high detections <-> pool on 1 - IoU fused with
+    the detection score (Hungarian, minimum_matching_threshold); 2nd association the still-unmatched TRACKED tracks <->
+    low detections (0.5); the rest of those become lost; unconfirmed tracks (one frame old) <-> leftover high detections
+    (0.7), unmatched ones are removed; leftover detections with score >= threshold + 0.1 start new tracks, which are
+    confirmed at their next match (immediately on the very first frame); lost tracks older than lost_track_buffer are
+    removed; tracked/lost duplicates with IoU > 0.85 are pruned (the younger one).  Output = input detections that
+    match an active track (IoU > 0.5, Hungarian), with `tracker_id` set; ids count from 1.
+
+    Restated from the paper / public description (supervision is absent here), NOT validated against supervision's
+    own code: ids remain UNPINNED.  Stateful and sequential: runs on rank 0 over frame-ordered detections."""
 
     def __init__(self, track_activation_threshold: float = 0.25, lost_track_buffer: int = 30,
                  minimum_matching_threshold: float = 0.8, frame_rate: float = 30, **kw):
-        self.high = track_activation_threshold
+        self.track_activation_threshold = track_activation_threshold
+        self.minimum_matching_threshold = minimum_matching_threshold
         self.det_thresh = track_activation_threshold + 0.1
-        self.match = minimum_matching_threshold
-        self.max_lost = int(frame_rate / 30.0 * lost_track_buffer)
+        self.max_time_lost = int(frame_rate / 30.0 * lost_track_buffer)
+        self.kf = _KalmanXYAH()
         self.reset()
 
     def reset(self):
-        self.tracks = []  # dict(id, box, vel, lost, hits)
-        self.next_id = 1
-        self.frame = 0
+        self.frame_id = 0
+        self.tracked, self.lost, self.removed = [], [], []
+        self._next_id = 0
 
-    def _assign(self, tracks, boxes, thr):
-        from scipy.optimize import linear_sum_assignment
+    def _new_id(self):
+        self._next_id += 1
+        return self._next_id
 
-        if not tracks or len(boxes) == 0:
-            return [], list(range(len(tracks))), list(range(len(boxes)))
-        pred = np.stack([t["box"] + t["vel"] for t in tracks])
-        cost = 1.0 - _iou_matrix(pred, boxes)
-        r, c = linear_sum_assignment(cost)
-        pairs = [(i, j) for i, j in zip(r, c) if cost[i, j] <= thr]
-        mi, mj = {i for i, _ in pairs}, {j for _, j in pairs}
-        return pairs, [i for i in range(len(tracks)) if i not in mi], [j for j in range(len(boxes)) if j not in mj]
+    def _update(self, boxes, scores, class_ids):
+        self.frame_id += 1
+        activated, refind, lost_now, removed_now = [], [], [], []
+        high = scores > self.track_activation_threshold
+        second = (scores > 0.1) & (scores < self.track_activation_threshold)
+        dets = [_STrack(boxes[i], scores[i], class_ids[i], i) for i in np.where(high)[0]]
+        dets2 = [_STrack(boxes[i], scores[i], class_ids[i], i) for i in np.where(second)[0]]
+        unconfirmed = [t for t in self.tracked if not t.is_activated]
+        tracked = [t for t in self.tracked if t.is_activated]
+        pool = _joint(tracked, self.lost)
+        for t in pool:  # multi_predict: lost tracks keep their height (velocity of h zeroed)
+            m = t.mean.copy()
+            if t.state != _TRACKED:
+                m[7] = 0
+            t.mean, t.cov = self.kf.predict(m, t.cov)
+        cost = _fuse_score(_iou_distance(pool, dets), dets)
+        matches, u_track, u_det = _linear_assignment(cost, self.minimum_matching_threshold)
+        for it, idt in matches:
+            t = pool[it]
+            if t.state == _TRACKED:
+                t.update(dets[idt], self.frame_id)
+                activated.append(t)
+            else:
+                t.re_activate(dets[idt], self.frame_id)
+                refind.append(t)
+        r_tracked = [pool[i] for i in u_track if pool[i].state == _TRACKED]
+        matches, u_track2, _ = _linear_assignment(_iou_distance(r_tracked, dets2), 0.5)
+        for it, idt in matches:
+            t = r_tracked[it]
+            if t.state == _TRACKED:
+                t.update(dets2[idt], self.frame_id)
+                activated.append(t)
+            else:
+                t.re_activate(dets2[idt], self.frame_id)
+                refind.append(t)
+        for it in u_track2:
+            t = r_tracked[it]
+            if t.state != _LOST:
+                t.state = _LOST
+                lost_now.append(t)
+        rest = [dets[i] for i in u_det]
+        cost = _fuse_score(_iou_distance(unconfirmed, rest), rest)
+        matches, u_unc, u_det = _linear_assignment(cost, 0.7)
+        for it, idt in matches:
+            unconfirmed[it].update(rest[idt], self.frame_id)
+            activated.append(unconfirmed[it])
+        for it in u_unc:
+            unconfirmed[it].state = _REMOVED
+            removed_now.append(unconfirmed[it])
+        for i in u_det:
+            d = rest[i]
+            if d.score < self.det_thresh:
+                continue
+            d.activate(self.kf, self.frame_id, self._new_id())
+            activated.append(d)
+        for t in self.lost:
+            if self.frame_id - t.frame_id > self.max_time_lost:
+                t.state = _REMOVED
+                removed_now.append(t)
+        self.tracked = [t for t in self.tracked if t.state == _TRACKED]
+        self.tracked = _joint(_joint(self.tracked, activated), refind)
+        self.lost = _sub(self.lost, self.tracked)
+        self.lost.extend(lost_now)
+        self.lost = _sub(self.lost, self.removed)
+        self.removed.extend(removed_now)
+        # duplicate pruning: of a tracked/lost pair with IoU > 0.85 the one with the shorter history goes
+        if self.tracked and self.lost:
+            pd = _iou_distance(self.tracked, self.lost)
+            da, db = set(), set()
+            for p, q in zip(*np.where(pd < 0.15)):
+                tp = self.tracked[p].frame_id - self.tracked[p].start_frame
+                tq = self.lost[q].frame_id - self.lost[q].start_frame
+                (db if tp > tq else da).add(int(q) if tp > tq else int(p))
+            self.tracked = [t for i, t in enumerate(self.tracked) if i not in da]
+            self.lost = [t for i, t in enumerate(self.lost) if i not in db]
+        return [t for t in self.tracked if t.is_activated]
 
     def update_with_detections(self, detections: Detections) -> Detections:
-        self.frame += 1
-        boxes = detections.xyxy.astype(np.float32)
-        conf = detections.confidence if detections.confidence is not None else np.ones(len(boxes), np.float32)
-        hi = np.where(conf > self.high)[0]
-        lo = np.where((conf > 0.1) & (conf <= self.high))[0]
-        ids = np.full(len(boxes), -1, dtype=int)
-        pairs, un_t, un_d = self._assign(self.tracks, boxes[hi], self.match)
-        for ti, dj in pairs:
-            self._hit(self.tracks[ti], boxes[hi[dj]])
-            ids[hi[dj]] = self.tracks[ti]["id"]
-        rem = [self.tracks[i] for i in un_t if self.tracks[i]["lost"] == 0]
-        pairs2, _, _ = self._assign(rem, boxes[lo], 0.5)
-        matched2 = set()
-        for ti, dj in pairs2:
-            self._hit(rem[ti], boxes[lo[dj]])
-            ids[lo[dj]] = rem[ti]["id"]
-            matched2.add(id(rem[ti]))
-        for i in un_t:
-            t = self.tracks[i]
-            if id(t) not in matched2:
-                t["lost"] += 1
-        for dj in un_d:
-            d = hi[dj]
-            if conf[d] >= self.det_thresh:
-                self.tracks.append(dict(id=self.next_id, box=boxes[d].copy(), vel=np.zeros(4, np.float32), lost=0,
-                                        hits=1))
-                if self.frame == 1:
-                    ids[d] = self.next_id
-                self.next_id += 1
-        self.tracks = [t for t in self.tracks if t["lost"] <= self.max_lost]
-        keep = ids >= 0
-        out = detections[np.where(keep)[0]]
+        n = len(detections)
+        boxes = np.asarray(detections.xyxy, dtype=np.float64).reshape(-1, 4)
+        scores = np.asarray(detections.confidence if detections.confidence is not None else np.ones(n), dtype=np.float64)
+        cls = np.asarray(detections.class_id if detections.class_id is not None else np.zeros(n, int))
+        tracks = self._update(boxes, scores, cls)
+        ids = np.full(n, -1, dtype=int)
+        if tracks and n:
+            cost = 1.0 - _iou_matrix(boxes, [t.tlbr for t in tracks])
+            matches, _, _ = _linear_assignment(cost, 0.5)
+            for i_det, i_trk in matches:
+                ids[i_det] = tracks[i_trk].track_id
+        keep = np.where(ids != -1)[0]
+        out = detections[keep]
         out.tracker_id = ids[keep]
         return out
-
-    @staticmethod
-    def _hit(t, box):
-        t["vel"] = 0.5 * t["vel"] + 0.5 * (box - t["box"])
-        t["box"] = box.copy()
-        t["lost"] = 0
-        t["hits"] += 1
 
 
 if HAVE_SUPERVISION:  # pragma: no cover

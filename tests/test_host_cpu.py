@@ -391,3 +391,40 @@ def test_weight_folding_and_packing_layouts():
                 assert torch.equal(sp[r, :6, s * 4 + c], ws[:, c, r, s].half())
     assert torch.count_nonzero(sp[:, :, 3::4]) == 0 and torch.count_nonzero(sp[:, :, 12:]) == 0
     assert torch.equal(sb[:6], torch.arange(6.0))
+
+
+def test_bytetrack_follows_the_published_algorithm():
+    """sv_compat.ByteTrack: ids from 1, a new track is confirmed at its second frame (immediately on frame 1), an
+    occluded track is re-identified from the lost pool through its Kalman prediction, low-score detections only extend
+    existing tracks, detections without a track are dropped, reset() restarts the ids."""
+    rng = np.random.default_rng(0)
+    base = np.array([[100, 100, 160, 260], [400, 120, 470, 300], [800, 500, 880, 700], [1200, 400, 1270, 600]], float)
+    bt = sv.ByteTrack(frame_rate=30)
+    seen = {}
+    for f in range(40):
+        b = base + np.array([3 * f, f, 3 * f, f]) + rng.normal(0, 1.5, (4, 4))
+        keep = np.ones(4, bool)
+        if 10 <= f < 14:
+            keep[1] = False  # occlusion of track 2
+        conf = np.full(4, 0.8)
+        if f == 30:
+            conf[2] = 0.2  # low-score detection of an existing track: second association keeps it
+        extra = np.array([[50 + f, 900, 90 + f, 1000]]) if f in (20, 21, 22) else np.zeros((0, 4))
+        lowonly = np.array([[1500, 100, 1560, 200]]) if f == 5 else np.zeros((0, 4))  # low score, no track: dropped
+        xy = np.vstack([b[keep], extra, lowonly])
+        cf = np.r_[conf[keep], np.full(len(extra), 0.9), np.full(len(lowonly), 0.2)]
+        out = bt.update_with_detections(sv.Detections(xyxy=xy.astype(np.float32), confidence=cf.astype(np.float32),
+                                                      class_id=np.zeros(len(xy), int)))
+        seen[f] = out.tracker_id.tolist()
+    assert seen[0] == [1, 2, 3, 4] and seen[9] == [1, 2, 3, 4]
+    assert seen[10] == [1, 3, 4] and seen[13] == [1, 3, 4]
+    assert seen[14] == [1, 2, 3, 4]  # re-identified, same id
+    assert seen[5] == [1, 2, 3, 4]
+    assert seen[20] == [1, 2, 3, 4] and seen[21] == [1, 2, 3, 4, 5] and seen[23] == [1, 2, 3, 4]
+    assert seen[30] == [1, 2, 3, 4]
+    bt.reset()
+    out = bt.update_with_detections(sv.Detections(xyxy=base.astype(np.float32), confidence=np.full(4, 0.9, np.float32),
+                                                  class_id=np.zeros(4, int)))
+    assert out.tracker_id.tolist() == [1, 2, 3, 4]
+    p = Player.from_json({"id": None, "xyxy": [1.0, 2.0, 3.0, 4.0], "projection": None, "class_id": 0, "confidence": 0.5})
+    assert p.id is None and Player.from_json(p.serialize()).serialize() == p.serialize()
