@@ -389,6 +389,9 @@ def main():
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(max(ms_e2e, wall_e2e * 1e3) / args.steps, 3)},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "timing": {"device_ms_per_step": round(ms_dev / args.steps, 3), "wall_ms_per_step": round(wall_dev * 1e3 / args.steps, 3),
+                       "e2e_device_ms_per_step": round(ms_e2e / args.steps, 3),
+                       "e2e_wall_ms_per_step": round(wall_e2e * 1e3 / args.steps, 3)},
         }), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -62,25 +62,6 @@ def _standardise(conv: nn.Conv2d, x: torch.Tensor, mean: float, std: float, rows
     conv.bias.data[sel] = mean - float(zs.mean()) * scale
 
 
-@torch.no_grad()
-def _unimodal_dfl(conv: nn.Conv2d, x: torch.Tensor, mean_bins: float, std_bins: float, v: float = 0.5):
-    """Shape the final box conv (cmid -> 4 x 16 DFL logits) like a TRAINED YOLOv8 head: per side s the logits are
-        logit_i = i * u_s(x) - v * i^2  =  -v (i - u_s / 2v)^2 + const,
-    a discretised Gaussian (sigma^2 = 1 / 2v bins) centred at u_s(x) / 2v, where u_s is a random linear read-out of
-    the features standardised to `mean_bins` +- `std_bins` on the calibration input.  Trained DFL distributions are
-    unimodal over neighbouring bins; i.i.d. random logits are multi-modal (mass on far-apart bins), which makes the
-    expectation -- the box edge -- hypersensitive to 1e-2 logit noise in a way no trained checkpoint is."""
-    w, b = conv.weight.data, conv.bias.data
-    for s_ in range(4):
-        d = w[s_ * 16].clone()  # (cmid,1,1): the random direction of this side
-        z = torch.nn.functional.conv2d(x, d[None])
-        scale = 2 * v * std_bins / float(z.std().clamp_min(1e-6))
-        shift = 2 * v * mean_bins - float(z.mean()) * scale
-        for i in range(16):
-            w[s_ * 16 + i] = i * scale * d
-            b[s_ * 16 + i] = i * shift - v * i * i
-
-
 def make_tracknet(seed: int = SEEDS["tracknet"], frac_above: float = 1e-2) -> dict:
     """Random TrackNet whose heat-maps cross 0.5 on roughly `frac_above` of the pixels (a few blobs per frame)."""
     g = torch.Generator().manual_seed(seed)
@@ -115,7 +96,7 @@ def calib_from_frame(frame_bgr, imgsz: int = 640) -> torch.Tensor:
 
 
 def make_yolo(kind: str, scale: str = "n", seed: int | None = None, cls_mean: float | None = None,
-              calib: torch.Tensor | None = None, dfl: str = "unimodal") -> dict:
+              calib: torch.Tensor | None = None) -> dict:
     """kind: 'detect' (nc=80), 'pose13' (nc=1, 13x3 kpts), 'court12' (nc=1, 12x3 kpts).  Last layers are
     standardised on a calibration image so that O(1%) of the anchors exceed the trackers' confidence thresholds
      with varied box sizes; for 'detect' class 0 (person) dominates the other 79."""
@@ -134,10 +115,7 @@ def make_yolo(kind: str, scale: str = "n", seed: int | None = None, cls_mean: fl
         with torch.no_grad():
             hb = head.cv2[l][1](head.cv2[l][0](feats[l]))
             hc = head.cv3[l][1](head.cv3[l][0](feats[l]))
-        if dfl == "unimodal":  # trained-like DFL: one bump per side, centre 4 +- 2.5 bins -> varied box sizes
-            _unimodal_dfl(head.cv2[l][2], hb, mean_bins=4.0, std_bins=2.5)
-        else:  # "random": i.i.d. logits, multi-modal distributions (adversarial for box-edge precision; diagnostics)
-            _standardise(head.cv2[l][2], hb, mean=0.0, std=2.5)
+        _standardise(head.cv2[l][2], hb, mean=0.0, std=2.5)  # peaky DFL distributions -> varied box sizes
         if nc > 1:
             _standardise(head.cv3[l][2], hc, mean=-7.0, std=1.0, rows=slice(1, nc))
             _standardise(head.cv3[l][2], hc, mean=cls_mean, std=1.3, rows=slice(0, 1))

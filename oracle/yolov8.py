@@ -133,9 +133,10 @@ class DetectHead(nn.Module):
         x = torch.cat([r[:, : 64 + self.nc].reshape(B, 64 + self.nc, -1) for r in raws], 2)
         box, cls = x.split((64, self.nc), 1)
         anc, st = self.anchors([r.shape[2:] for r in raws], self.strides)
+        anc, st = anc.to(box.device), st.to(box.device)
         b, _, a = box.shape
         dist = box.view(b, 4, 16, a).transpose(2, 1).softmax(1)
-        dist = (dist * torch.arange(16, dtype=torch.float32).view(1, 16, 1, 1)).sum(1)  # DFL expectation
+        dist = (dist * torch.arange(16, dtype=torch.float32, device=box.device).view(1, 16, 1, 1)).sum(1)  # DFL expectation
         lt, rb = dist.chunk(2, 1)
         x1y1, x2y2 = anc.unsqueeze(0) - lt, anc.unsqueeze(0) + rb
         dbox = torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), 1) * st

@@ -1,8 +1,7 @@
 """Noise floor of the REFERENCE's own GPU numerics: the oracle network (= what ultralytics runs) executed by PyTorch
 eager on the B200 with cuDNN TF32 convolutions (torch's default, i.e. the reference's GPU path) and in strict fp32,
 each compared with the CPU fp32 oracle under the same borderline-exclusion protocol (tests/parity.py) that the engine
-is held to.  Also reports the engine itself on the same inputs.  Heads: dfl='random' (i.i.d. DFL logits, round-1
-checkpoints) and dfl='unimodal' (trained-like).  Usage: python scripts/diag_tf32_floor.py [B]"""
+is held to.  Also reports the engine itself on the same inputs.  Usage: python scripts/diag_tf32_floor.py [B]"""
 import sys
 
 import cv2
@@ -43,16 +42,16 @@ def results_from_pred(net, pred, x, ims_hw, conf, classes, max_det):
 
 def summary(tag, reps):
     ns = sum(r.n_sure for r in reps)
-    print(f"  {tag:34s} sure {ns:4d}  unmatched-sure {sum(len(r.sure_unmatched) for r in reps):3d}  extras "
+    print(f"  {tag:34s} sure {ns:4d} (ill-cond. {sum(r.n_reg for r in reps):3d})  unmatched-sure {sum(len(r.sure_unmatched) for r in reps):3d}  extras "
           f"{sum(len(r.extras) for r in reps):3d}  min IoU {min(r.min_iou_sure for r in reps):.4f}  max dconf "
           f"{max(r.max_conf_err for r in reps):.4f}  max kpt {max(r.max_kpt_px for r in reps):.3f} px", flush=True)
 
 
-for dfl in ("random", "unimodal"):
+for dfl in ("random",):
     for scale, kind, imgsz, prep in (("n", "detect", 640, "letterbox_q1"), ("n", "pose13", 1280, "pil_square"),
                                      ("n", "court12", 640, "pil_square"), ("m", "detect", 640, "letterbox_q1"),
                                      ("m", "court12", 640, "pil_square")):
-        ck = OW.make_yolo(kind, scale=scale, dfl=dfl)
+        ck = OW.make_yolo(kind, scale=scale)
         net = OW.load_yolo(ck)
         conf = {"detect": 0.5, "pose13": 0.25, "court12": 0.5}[kind]
         classes = [0] if kind != "court12" else None
