@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--res", default="1080p", choices=list(RES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-host", action="store_true", help="cProfile the timed region's host side (stderr)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -295,7 +296,16 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    if args.profile_host:
+        import cProfile
+        import pstats
+
+        pr = cProfile.Profile()
+        pr.enable()
     ms_dev, wall_dev, launches, ndet = timed(dev_batches, args.steps)
+    if args.profile_host:
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(35)
     run_steps(host_batches, 2)
     ms_e2e, wall_e2e, _, _ = timed(host_batches, args.steps)
     clocks = sampler.stop() if rank == 0 else None

@@ -57,9 +57,10 @@ typedef struct pb_conv_desc {
   const float* bias;  /* float [cout_pad] (folded BN shift or conv bias)                       */
   int cout_pad;       /* multiple of 16                                                        */
   int ksize;          /* 1 or 3 (padding = ksize/2)                                            */
-  int stride;         /* 1 or 2 (stride 2 needs even H and W)                                  */
+  int stride;         /* 1 or 2 (stride 2 needs even H and W; with ksize 1 it reads every second pixel) */
   int act;            /* PB_ACT_*                                                              */
-  const void* res;    /* optional half NHWC residual added after the activation, or NULL       */
+  const void* res;    /* optional half NHWC residual, or NULL; added after the activation (ultralytics Bottleneck:
+                         x + cv2(cv1(x))) unless res_before_act is set                         */
   int res_C, res_coff;
   void* out;
   int out_C;      /* channel stride of the output tensor (elements)                            */
@@ -79,6 +80,9 @@ typedef struct pb_conv_desc {
    * C = 4, cin = 16, weight = half [3 filter rows][cout_pad][16] with k = s*4 + c (s = filter column, c = channel;
    * k >= 12 and c == 3 are zero).  One TMA box of overlapping 16-element rows serves all three filter rows.  */
   int in_layout;
+  /* 1: out = act(conv + bias + res) -- the torchvision ResNet Bottleneck (relu(bn3(conv3) + identity), the court
+   * regressor of keypoints_tracker.py:158-167); 0: out = act(conv + bias) + res.                                 */
+  int res_before_act;
 } pb_conv_desc;
 
 /* One-shot launches (plan + run). The *_reference variant is a plain CUDA-core kernel used by tests to
@@ -161,6 +165,36 @@ int pb_yolo_decode(const pb_yolo_level* levels, int nlevels, int B, int fC, int 
 size_t pb_yolo_nms_scratch_bytes(int B, int cap);
 int pb_yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count, int B, int cap, int rowlen,
                 float iou, int max_det, float* out, int* out_count, void* scratch, void* stream);
+
+/* ---- ResNet50 court-keypoint regressor: the non-3x3/1x1 pieces (keypoints_tracker.py:158-167,276-312;
+ *      keypoints_tracker/iterable.py:10-41).  The bottleneck stacks are pb_conv2d programs (res_before_act = 1). ---- */
+/* ToTensor + Normalize: src u8 (npix,3) RGB -> dst half (npix,4) = ((x/255) - mean[c]) / std[c], channel 3 = 0.
+ * mean3 / std3: HOST float[3].                                                                                  */
+int pb_u8_normalize_f16(const uint8_t* src, long long npix, const float* mean3, const float* std3, void* dst,
+                        void* stream);
+/* conv1: 7x7 / stride 2 / pad 3, 3 -> 64, + bias (folded BN) + ReLU.  in half (N,H,W,4) (channel 3 ignored),
+ * weight float [(r*7+s)*3+c][64], bias float [64], out half NHWC (N,H/2,W/2,64).                                 */
+int pb_resnet_stem7x7(const void* in, int N, int H, int W, const float* weight, const float* bias, void* out,
+                      void* stream);
+/* MaxPool2d(3, stride 2, padding 1): half NHWC (N,H,W,C) -> (N,(H-1)/2+1,(W-1)/2+1,C), C % 8 == 0.             */
+int pb_maxpool3x3s2(const void* in, int N, int H, int W, int C, void* out, void* stream);
+/* AdaptiveAvgPool2d(1) + Linear(C -> n_out) + Sigmoid: in half (N,HW,C), weight float [n_out][C], bias float [n_out],
+ * out float (N,n_out).                                                                                          */
+int pb_avgpool_fc_sigmoid(const void* in, int N, int HW, int C, const float* weight, const float* bias, int n_out,
+                          float* out, void* stream);
+
+/* ---- ByteTrack on the host (players_tracker.py:311,367-369: sv.ByteTrack(frame_rate).update_with_detections) ----
+ * The order-dependent stage after the players detector, in C++ (no CUDA): Kalman xyah filter, two-stage Hungarian
+ * association on 1 - IoU (fused with the score in the first stage), unconfirmed-track handling, lost-track buffer,
+ * duplicate pruning; ids count from 1.  One handle per video; frames must be fed in order.                        */
+typedef struct pb_bytetrack pb_bytetrack;
+pb_bytetrack* pb_bytetrack_create(double track_activation_threshold, int lost_track_buffer,
+                                  double minimum_matching_threshold, double frame_rate);
+void pb_bytetrack_destroy(pb_bytetrack* bt);
+void pb_bytetrack_reset(pb_bytetrack* bt);
+/* One frame: boxes float (n,4) xyxy, scores float (n) (HOST pointers) -> ids_out int (n): the track id attached to each
+ * detection, -1 for detections without an active track (dropped by update_with_detections).                      */
+int pb_bytetrack_update(pb_bytetrack* bt, const float* boxes, const float* scores, int n, int* ids_out);
 
 /* ---- InpaintNet (ball_tracker/models.py:101-130, called at ball_tracker.py:573-576) ----------------------- */
 /* coor float (N,L,2) normalised coordinates, mask float (N,L) inpaint mask -> out float (N,L,2) = sigmoid(net).

@@ -30,6 +30,7 @@ class ConvDesc(C.Structure):
         ("cout_store", C.c_int),
         ("head_weight", C.c_void_p), ("head_bias", C.c_void_p), ("head_n", C.c_int), ("head_out", C.c_void_p),
         ("in_layout", C.c_int),
+        ("res_before_act", C.c_int),
     ]
 
 
@@ -68,6 +69,14 @@ SIGNATURES = {
                              _i, _p]),
     "pb_yolo_nms_scratch_bytes": (C.c_size_t, [_i, _i]),
     "pb_yolo_nms": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p, _p, _p]),
+    "pb_u8_normalize_f16": (_i, [_p, C.c_longlong, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p]),
+    "pb_resnet_stem7x7": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
+    "pb_maxpool3x3s2": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "pb_avgpool_fc_sigmoid": (_i, [_p, _i, _i, _i, _p, _p, _i, _p, _p]),
+    "pb_bytetrack_create": (_p, [C.c_double, _i, C.c_double, C.c_double]),
+    "pb_bytetrack_destroy": (None, [_p]),
+    "pb_bytetrack_reset": (None, [_p]),
+    "pb_bytetrack_update": (_i, [_p, _p, _p, _i, _p]),
     "pb_inpaintnet_forward": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "pb_median_u8": (_i, [_p, _i, C.c_longlong, _p, _i, _p]),
     "pb_tracknet_ensemble": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p]),

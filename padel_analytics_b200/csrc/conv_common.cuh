@@ -8,7 +8,7 @@ namespace pb {
 // bias + activation on 16 accumulator columns; `act` is CTA-uniform and each case is a straight unrolled loop so
 // the 16 independent MUFU chains interleave
 __device__ __forceinline__ void bias_act16(const uint32_t (&r)[16], const float* __restrict__ sbias, int act,
-                                           float (&v)[16]) {
+                                           float (&v)[16], const __half* __restrict__ res_first = nullptr) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * q);
@@ -16,6 +16,10 @@ __device__ __forceinline__ void bias_act16(const uint32_t (&r)[16], const float*
     v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b.y;
     v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
     v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
+  }
+  if (res_first != nullptr) {  // ResNet: the identity joins before the activation
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += __half2float(res_first[j]);
   }
   if (act == PB_ACT_SILU) {
 #pragma unroll
@@ -45,7 +49,7 @@ struct EpiPix {
 // residual / fused head / store of 16 activated channels starting at output channel ch0 (c = column in the N tile)
 __device__ __forceinline__ void epilogue_store16(const ConvKParams& kp, const EpiPix& px, int ch0, int c,
                                                  float (&v)[16], float (&hacc)[8]) {
-  if (kp.res != nullptr) {
+  if (kp.res != nullptr && !kp.res_first) {
     const uint4* rp = reinterpret_cast<const uint4*>(kp.res + px.pix * kp.res_C + kp.res_coff + ch0);
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
@@ -181,7 +185,21 @@ struct EpiOut {
 };
 
 // bias + activation (+ residual) of one 16-column chunk of this thread's pixel
-__device__ __forceinline__ void epi_compute16(int act, bool has_res, bool plain_silu, uint32_t (&r)[16],
+__device__ __forceinline__ void epi_add_res16(const uint4 (&rv)[2], float (&v)[16]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const __half2* h2 = reinterpret_cast<const __half2*>(&rv[g]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h2[j]);
+      v[8 * g + 2 * j] += f.x;
+      v[8 * g + 2 * j + 1] += f.y;
+    }
+  }
+}
+
+// has_res: 0 none, 1 residual after the activation, 2 residual before it (CTA-uniform)
+__device__ __forceinline__ void epi_compute16(int act, int has_res, bool plain_silu, uint32_t (&r)[16],
                                               const float* __restrict__ sbias, const uint4 (&rv)[2], float (&v)[16]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -191,6 +209,7 @@ __device__ __forceinline__ void epi_compute16(int act, bool has_res, bool plain_
     v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
     v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
   }
+  if (has_res == 2) epi_add_res16(rv, v);
   if (act == PB_ACT_SILU) {  // CTA-uniform
     if (plain_silu) {
 #pragma unroll
@@ -206,21 +225,10 @@ __device__ __forceinline__ void epi_compute16(int act, bool has_res, bool plain_
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
   }
-  if (has_res) {
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const __half2* h2 = reinterpret_cast<const __half2*>(&rv[g]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h2[j]);
-        v[8 * g + 2 * j] += f.x;
-        v[8 * g + 2 * j + 1] += f.y;
-      }
-    }
-  }
+  if (has_res == 1) epi_add_res16(rv, v);
 }
 
-__device__ __forceinline__ void epi_chunk(int act, bool has_res, bool plain_silu, const EpiOut& eo, uint32_t (&r)[16],
+__device__ __forceinline__ void epi_chunk(int act, int has_res, bool plain_silu, const EpiOut& eo, uint32_t (&r)[16],
                                           const float* __restrict__ sbias, char* op, const uint4 (&rv)[2], bool valid,
                                           int nvalid) {
   float v[16];
@@ -266,7 +274,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOu
                                               uint32_t valid_mask) {
   uint32_t ra[16], rb[16];
   const int act = kp.act;
-  const bool has_res = kp.res != nullptr;
+  const int has_res = kp.res != nullptr ? (kp.res_first ? 2 : 1) : 0;
   const bool plain_silu = (kp.dbg_flags & 1) != 0;
   const int cbytes = eo.mode == PB_OUT_F32_NHWC ? 64 : 32;  // bytes of one 16-channel chunk in the output
   int j = 0, c = 0;

@@ -323,12 +323,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tmem_ld_wait();
           if (px.valid && c < kp.cout_store) {
             float v[16];
-            bias_act16(r0, tail->bias + c, kp.act, v);
+            bias_act16(r0, tail->bias + c, kp.act, v,
+                       (kp.res && kp.res_first) ? kp.res + px.pix * kp.res_C + kp.res_coff + c : nullptr);
             epilogue_store16(kp, px, c, c, v, hacc);
           }
           if (second && px.valid && c + 16 < kp.cout_store) {
             float v[16];
-            bias_act16(r1, tail->bias + c + 16, kp.act, v);
+            bias_act16(r1, tail->bias + c + 16, kp.act, v,
+                       (kp.res && kp.res_first) ? kp.res + px.pix * kp.res_C + kp.res_coff + c + 16 : nullptr);
             epilogue_store16(kp, px, c + 16, c + 16, v, hacc);
           }
         }

@@ -254,12 +254,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int ch0 = tc.nt * kp.BN + c;
         if (px.valid && ch0 < kp.cout_store) {
           float v[16];
-          bias_act16(r0, sb + c, kp.act, v);
+          bias_act16(r0, sb + c, kp.act, v,
+                     (kp.res && kp.res_first) ? kp.res + px.pix * kp.res_C + kp.res_coff + ch0 : nullptr);
           epilogue_store16(kp, px, ch0, c, v, hacc);
         }
         if (second && px.valid && ch0 + 16 < kp.cout_store) {
           float v[16];
-          bias_act16(r1, sb + c + 16, kp.act, v);
+          bias_act16(r1, sb + c + 16, kp.act, v,
+                     (kp.res && kp.res_first) ? kp.res + px.pix * kp.res_C + kp.res_coff + ch0 + 16 : nullptr);
           epilogue_store16(kp, px, ch0 + 16, c + 16, v, hacc);
         }
       }
@@ -325,7 +327,6 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
   const bool stem = d->in_layout == PB_IN_STEM4;
   PB_CHECK(d->ksize == 1 || d->ksize == 3, "conv: ksize %d unsupported", d->ksize);
   PB_CHECK(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
-  PB_CHECK(!(d->stride == 2 && d->ksize == 1), "conv: 1x1 stride-2 unsupported");
   PB_CHECK(d->cin > 0 && d->cin % 16 == 0, "conv: cin %d must be a positive multiple of 16", d->cin);
   PB_CHECK(d->cout_pad <= kConvMaxCout, "conv: cout_pad %d > %d", d->cout_pad, kConvMaxCout);
   PB_CHECK(d->cout_pad > 0 && d->cout_pad % 16 == 0, "conv: cout_pad %d must be a multiple of 16", d->cout_pad);
@@ -375,6 +376,7 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
   kp.res = reinterpret_cast<const __half*>(d->res);
   kp.res_C = d->res_C;
   kp.res_coff = d->res_coff;
+  kp.res_first = d->res_before_act ? 1 : 0;
   kp.out = d->out;
   kp.out_C = d->out_C;
   kp.out_coff = d->out_coff;
@@ -573,11 +575,13 @@ __global__ void conv_reference_kernel(pb_conv_desc d, int Ho, int Wo) {
         for (int c = 0; c < d.cin; ++c) acc += __half2float(ip[c]) * __half2float(wp[c]);
       }
     float v = acc + d.bias[co];
+    const size_t pix = ((size_t)n * Ho + oh) * Wo + ow;
+    const float resv = d.res ? __half2float(reinterpret_cast<const __half*>(d.res)[pix * d.res_C + d.res_coff + co]) : 0.f;
+    if (d.res_before_act) v += resv;
     if (d.act == PB_ACT_RELU) v = fmaxf(v, 0.f);
     else if (d.act == PB_ACT_SILU) v = v / (1.f + expf(-v));
     else if (d.act == PB_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
-    const size_t pix = ((size_t)n * Ho + oh) * Wo + ow;
-    if (d.res) v += __half2float(reinterpret_cast<const __half*>(d.res)[pix * d.res_C + d.res_coff + co]);
+    if (!d.res_before_act) v += resv;
     if (d.out_mode == PB_OUT_F16_NHWC) {
       reinterpret_cast<__half*>(d.out)[pix * d.out_C + d.out_coff + co] = __float2half_rn(v);
     } else if (d.out_mode == PB_OUT_F16_NHWC_UP2) {

@@ -88,7 +88,7 @@ inline int conv_pick_egroups(int acc_stages) {
   if (want > acc_stages) want = acc_stages;
   return want < 1 ? 1 : want;
 }
-constexpr int kConvMaxCout = 1024;
+constexpr int kConvMaxCout = 2048;  // ResNet50 layer4 (keypoints_tracker.py:158)
 
 // Division by a launch-time constant as multiply-high + shift (dividend < 2^31): the per-tile coordinate decode of the
 // persistent kernels would otherwise spend ~25 instructions per runtime `/` or `%` in every warp, every tile.
@@ -125,6 +125,7 @@ struct ConvKParams {
   int act;
   const __half* res;
   int res_C, res_coff;
+  int res_first;  // 1: residual added before the activation (ResNet), 0: after (YOLO Bottleneck)
   void* out;
   int out_C, out_coff, out_mode, cout_store;
   uint32_t idesc;

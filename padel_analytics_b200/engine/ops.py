@@ -43,7 +43,7 @@ def pack_conv_weight(w: torch.Tensor, b: torch.Tensor | None, cin_pad: int, cout
 def make_conv_desc(x: torch.Tensor, c_in_off: int, cin: int, w: torch.Tensor, b: torch.Tensor, ksize: int,
                    stride: int, act: int, out: torch.Tensor, out_coff: int, out_mode: int = L.OUT_F16_NHWC,
                    cout_store: int | None = None, res: torch.Tensor | None = None, res_coff: int = 0,
-                   head: tuple | None = None) -> L.ConvDesc:
+                   head: tuple | None = None, res_before_act: bool = False) -> L.ConvDesc:
     """x: NHWC half tensor (N,H,W,C). w: packed half [taps][cout_pad][cin]. out: NHWC tensor (half or float), or
     (N,C,H,W) float for OUT_F32_NCHW."""
     N, H, W, Ct = x.shape
@@ -55,6 +55,7 @@ def make_conv_desc(x: torch.Tensor, c_in_off: int, cin: int, w: torch.Tensor, b:
     d.c_in_off, d.cin = c_in_off, cin
     d.weight, d.bias = w.data_ptr(), b.data_ptr()
     d.cout_pad, d.ksize, d.stride, d.act = cout_pad, ksize, stride, act
+    d.res_before_act = 1 if res_before_act else 0
     if res is not None:
         d.res, d.res_C, d.res_coff = res.data_ptr(), res.shape[-1], res_coff
     else:

@@ -70,10 +70,22 @@ def _bicubic(x: float) -> float:
     return 0.0
 
 
-def pil_bicubic_tables(in_size: int, out_size: int):
+def _bilinear(x: float) -> float:
+    if x < 0.0:
+        x = -x
+    return 1.0 - x if x < 1.0 else 0.0
+
+
+def pil_bilinear_tables(in_size: int, out_size: int):
+    """Same for Image.BILINEAR (support 1): torchvision transforms.Resize on a PIL image
+    (/root/reference/trackers/keypoints_tracker/iterable.py:19)."""
+    return pil_bicubic_tables(in_size, out_size, support0=1.0, filt=_bilinear)
+
+
+def pil_bicubic_tables(in_size: int, out_size: int, support0: float = 2.0, filt=None):
     """Pillow precompute_coeffs + normalize_coeffs_8bpc for the full-image box.
     Returns (bounds int32[out,2] = (xmin, xsize), kk int32[out,ksize], ksize)."""
-    support0 = 2.0
+    filt = filt or _bicubic
     scale = in_size / out_size
     filterscale = scale if scale >= 1.0 else 1.0
     support = support0 * filterscale
@@ -93,7 +105,7 @@ def pil_bicubic_tables(in_size: int, out_size: int):
         xmax -= xmin
         k = [0.0] * ksize
         for x in range(xmax):
-            w = _bicubic((x + xmin - center + 0.5) * ss)
+            w = filt((x + xmin - center + 0.5) * ss)
             k[x] = w
             ww += w
         for x in range(xmax):

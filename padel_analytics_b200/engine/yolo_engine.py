@@ -401,38 +401,44 @@ class YoloEngine:
 
     def _results(self, rows, counts, n, net_hw, orig_hw):
         """scale_boxes / scale_coords / clip / keypoint conf<0.5 -> 0 (ultralytics ops, SURVEY App. A.4 vi-vii),
-        float32 arithmetic on the host (a few dozen numbers per image)."""
+        float32 arithmetic on the host, one vectorised pass over the whole (n, max_det, 6+nk) block (the padding rows
+        beyond each image's count are transformed too and never looked at)."""
         h1, w1 = net_hw
         h0, w0 = orig_hw
         gain = min(h1 / h0, w1 / w0)
         padb = (round((w1 - w0 * gain) / 2 - 0.1), round((h1 - h0 * gain) / 2 - 0.1))
         padk = ((w1 - w0 * gain) / 2, (h1 - h0 * gain) / 2)
         g32 = np.float32(gain)
+        r = rows[:n].astype(np.float32, copy=True)
+        box = r[..., :6]
+        box[..., [0, 2]] -= np.float32(padb[0])
+        box[..., [1, 3]] -= np.float32(padb[1])
+        box[..., :4] /= g32
+        box[..., 0] = np.clip(box[..., 0], 0, w0)
+        box[..., 2] = np.clip(box[..., 2], 0, w0)
+        box[..., 1] = np.clip(box[..., 1], 0, h0)
+        box[..., 3] = np.clip(box[..., 3], 0, h0)
+        kall = None
+        if self.kpt_shape:
+            K, D = self.kpt_shape
+            kall = r[..., 6:].reshape(n, r.shape[1], K, D)
+            kall[..., 0] -= np.float32(padk[0])
+            kall[..., 1] -= np.float32(padk[1])
+            kall[..., 0] /= g32
+            kall[..., 1] /= g32
+            kall[..., 0] = np.clip(kall[..., 0], 0, w0)
+            kall[..., 1] = np.clip(kall[..., 1], 0, h0)
+            if D == 3:
+                m = kall[..., 2] < 0.5
+                kall[..., 0][m] = 0
+                kall[..., 1][m] = 0
+        boxes_t = torch.from_numpy(np.ascontiguousarray(box))
+        kp_t = torch.from_numpy(np.ascontiguousarray(kall)) if kall is not None else None
         res = []
         for i in range(n):
-            r = rows[i, : counts[i]].astype(np.float32, copy=True)
-            box = r[:, :6].copy()
-            box[:, [0, 2]] -= np.float32(padb[0])
-            box[:, [1, 3]] -= np.float32(padb[1])
-            box[:, :4] /= g32
-            box[:, [0, 2]] = np.clip(box[:, [0, 2]], 0, w0)
-            box[:, [1, 3]] = np.clip(box[:, [1, 3]], 0, h0)
-            kp = None
-            if self.kpt_shape:
-                K, D = self.kpt_shape
-                k = r[:, 6:].reshape(-1, K, D).copy()
-                k[..., 0] -= np.float32(padk[0])
-                k[..., 1] -= np.float32(padk[1])
-                k[..., 0] /= g32
-                k[..., 1] /= g32
-                k[..., 0] = np.clip(k[..., 0], 0, w0)
-                k[..., 1] = np.clip(k[..., 1], 0, h0)
-                if D == 3:
-                    m = k[..., 2] < 0.5
-                    k[..., 0][m] = 0
-                    k[..., 1][m] = 0
-                kp = Keypoints(torch.from_numpy(k))
-            res.append(Result(Boxes(torch.from_numpy(box)), kp, self.names, (h0, w0)))
+            c = int(counts[i])
+            res.append(Result(Boxes(boxes_t[i, :c]), Keypoints(kp_t[i, :c]) if kp_t is not None else None, self.names,
+                              (h0, w0)))
         return res
 
     @torch.no_grad()

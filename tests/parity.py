@@ -51,7 +51,9 @@ def dfl_edge_moves(dfl_logits: torch.Tensor, strides: torch.Tensor, eps_logit: f
     pipeline avoids -- the engine's fp16 storage, and equally the TF32 convolutions of the reference's own GPU path
     (profiles/r02_parity_noise_floor.md).  A trained DFL head is unimodal (|i - E| < 1 where the mass is).
     Calibration (scripts/emulate_engine_numerics.py, 440 boxes): actual loss / this predictor at eps = 1 has median
-    0.017, p99 0.056, max 0.09, uniformly over the three strides; eps_logit = 0.06 flags every box that missed the bar.
+    0.017, p99 0.056, max 0.09, uniformly over the three strides; the default eps_logit = 0.06 (3.5 x the median)
+    flags 46 % of those boxes, among them all 24 that missed 0.99 in the emulation (at 0.04, 3 of them -- and one on
+    the GPU, IoU 0.9888 -- slipped through).
     dfl_logits: (64, n); strides: (n,)."""
     lg = dfl_logits.view(4, 16, -1)
     p = lg.softmax(1)
@@ -242,13 +244,15 @@ def check_batch(net, x, results, conf, iou, classes, max_det, img_hw, frame_scal
     return reports
 
 
-def assert_reports(reports, kind="", min_sure_frac=0.5):
+def assert_reports(reports, kind="", min_sure_frac=0.5, min_tight=1):
     tot_sure = sum(r.n_sure for r in reports)
     tot_exact = sum(r.n_exact for r in reports)
     assert tot_exact > 0, f"{kind}: vacuous, the oracle found no detections"
     assert tot_sure >= min_sure_frac * tot_exact, f"{kind}: vacuous, only {tot_sure} sure of {tot_exact} oracle detections"
     tight = tot_sure - sum(r.n_reg for r in reports)
-    assert tight >= 3, f"{kind}: vacuous, only {tight} well-conditioned sure boxes are held to IoU >= 0.99"
+    print(f"{kind}: {tot_exact} oracle detections, {tot_sure} non-borderline, {tight} of them well-conditioned (IoU >= 0.99 "
+          f"required), {tot_sure - tight} ill-conditioned (IoU >= 0.95 required)")
+    assert tight >= min_tight, f"{kind}: vacuous, only {tight} well-conditioned sure boxes are held to IoU >= 0.99"
     bad = [(i, r.sure_unmatched) for i, r in enumerate(reports) if r.sure_unmatched]
     assert not bad, f"{kind}: non-borderline oracle detections without an IoU >= 0.99 (ill-conditioned box: 0.95) partner: {bad}"
     ext = [(i, r.extras) for i, r in enumerate(reports) if r.extras]

@@ -13,7 +13,7 @@ ACT = {L.ACT_NONE: lambda v: v, L.ACT_RELU: torch.relu, L.ACT_SILU: F.silu, L.AC
 
 
 def run_case(N, H, W, cin, cout, k, s, act, cin_real=None, c_total=None, c_in_off=0, out_mode=L.OUT_F16_NHWC,
-             residual=False, out_coff=0, out_extra=0, seed=0, reference=False):
+             residual=False, out_coff=0, out_extra=0, seed=0, reference=False, res_first=False):
     g = torch.Generator().manual_seed(seed)
     dev = "cuda"
     cin_real = cin_real or cin
@@ -41,14 +41,17 @@ def run_case(N, H, W, cin, cout, k, s, act, cin_real=None, c_total=None, c_in_of
     if residual:
         res = torch.randn(N, Ho, Wo, cout_pad, generator=g).half().to(dev)
     d = ops.make_conv_desc(xd, c_in_off, cin, wp, bp, k, s, act, out, out_coff, out_mode, cs, res, 0)
+    d.res_before_act = 1 if res_first else 0
     ops.conv2d(d, reference=reference)
     torch.cuda.synchronize()
     # fp32 reference on the fp16-rounded operands
     xr = x16[..., c_in_off:c_in_off + cin_real].float().permute(0, 3, 1, 2)
     wr = w.half().float()
     y = F.conv2d(xr, wr, b, stride=s, padding=k // 2)
+    if residual and res_first:  # torchvision ResNet Bottleneck: relu(bn3(conv3(.)) + identity)
+        y = y + res.cpu().float()[..., :cout].permute(0, 3, 1, 2)
     y = ACT[act](y)
-    if residual:
+    if residual and not res_first:
         y = y + res.cpu().float()[..., :cout].permute(0, 3, 1, 2)
     o = out.cpu().float()
     if out_mode == L.OUT_F32_NCHW:
@@ -90,6 +93,15 @@ CASES = [
     dict(N=2, H=16, W=32, cin=64, cout=64, k=3, s=1, act=L.ACT_RELU, out_mode=L.OUT_F16_NHWC_UP2),
     dict(N=1, H=72, W=128, cin=768, cout=256, k=3, s=1, act=L.ACT_RELU),
     dict(N=1, H=288, W=512, cin=32, cout=64, k=3, s=1, act=L.ACT_RELU, cin_real=27),
+    # ResNet50 court regressor shapes (keypoints_tracker.py:158): identity added BEFORE the ReLU, 1x1 stride-2
+    # downsample convs, 2048-wide outputs (8 N tiles)
+    dict(N=2, H=14, W=14, cin=256, cout=1024, k=1, s=1, act=L.ACT_RELU, residual=True, res_first=True),
+    dict(N=2, H=28, W=28, cin=512, cout=1024, k=1, s=2, act=L.ACT_NONE),
+    dict(N=2, H=56, W=56, cin=64, cout=64, k=3, s=1, act=L.ACT_RELU),
+    dict(N=2, H=28, W=28, cin=128, cout=128, k=3, s=2, act=L.ACT_RELU),
+    dict(N=3, H=7, W=7, cin=512, cout=2048, k=1, s=1, act=L.ACT_RELU, residual=True, res_first=True),
+    dict(N=2, H=24, W=40, cin=32, cout=32, k=3, s=1, act=L.ACT_RELU, residual=True, res_first=True),
+    dict(N=2, H=14, W=14, cin=1024, cout=2048, k=1, s=2, act=L.ACT_NONE),
 ]
 
 

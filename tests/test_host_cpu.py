@@ -393,13 +393,14 @@ def test_weight_folding_and_packing_layouts():
     assert torch.equal(sb[:6], torch.arange(6.0))
 
 
-def test_bytetrack_follows_the_published_algorithm():
-    """sv_compat.ByteTrack: ids from 1, a new track is confirmed at its second frame (immediately on frame 1), an
+@pytest.mark.parametrize("impl", ["native", "python"])
+def test_bytetrack_follows_the_published_algorithm(impl):
+    """sv_compat.ByteTrack (C++, pb_bytetrack_*) and ByteTrackPy (numpy): ids from 1, a new track is confirmed at its second frame (immediately on frame 1), an
     occluded track is re-identified from the lost pool through its Kalman prediction, low-score detections only extend
     existing tracks, detections without a track are dropped, reset() restarts the ids."""
     rng = np.random.default_rng(0)
     base = np.array([[100, 100, 160, 260], [400, 120, 470, 300], [800, 500, 880, 700], [1200, 400, 1270, 600]], float)
-    bt = sv.ByteTrack(frame_rate=30)
+    bt = (sv.ByteTrack if impl == "native" else sv.ByteTrackPy)(frame_rate=30)
     seen = {}
     for f in range(40):
         b = base + np.array([3 * f, f, 3 * f, f]) + rng.normal(0, 1.5, (4, 4))
@@ -428,3 +429,31 @@ def test_bytetrack_follows_the_published_algorithm():
     assert out.tracker_id.tolist() == [1, 2, 3, 4]
     p = Player.from_json({"id": None, "xyxy": [1.0, 2.0, 3.0, 4.0], "projection": None, "class_id": 0, "confidence": 0.5})
     assert p.id is None and Player.from_json(p.serialize()).serialize() == p.serialize()
+
+
+def test_native_bytetrack_equals_the_python_restatement():
+    """pb_bytetrack_update (csrc/bytetrack.cu) vs sv_compat.ByteTrackPy on random multi-object sequences with
+    occlusions, low-score and spurious detections: identical kept detections and ids, frame for frame."""
+    def seq(seed, T=200):
+        rng = np.random.default_rng(seed)
+        K = int(rng.integers(3, 14))
+        pos, vel, size = rng.uniform(100, 1500, (K, 2)), rng.normal(0, 4, (K, 2)), rng.uniform(40, 220, (K, 2))
+        for _ in range(T):
+            pos = pos + vel + rng.normal(0, 1.0, (K, 2))
+            vis = rng.random(K) > 0.08
+            conf = np.clip(rng.normal(0.7, 0.25, K), 0.05, 0.99)
+            b = np.hstack([pos - size / 2, pos + size / 2]) + rng.normal(0, 1.5, (K, 4))
+            extra = rng.uniform(0, 1800, (int(rng.integers(0, 3)), 2))
+            eb = np.hstack([extra, extra + rng.uniform(30, 100, (len(extra), 2))])
+            yield (np.vstack([b[vis], eb]).astype(np.float32),
+                   np.r_[conf[vis], rng.uniform(0.1, 0.9, len(eb))].astype(np.float32))
+
+    frames = 0
+    for seed in range(8):
+        a, b = sv.ByteTrackPy(frame_rate=25.08), sv.ByteTrack(frame_rate=25.08)
+        for xy, cf in seq(seed):
+            mk = lambda: sv.Detections(xyxy=xy.copy(), confidence=cf.copy(), class_id=np.zeros(len(xy), int))
+            o1, o2 = a.update_with_detections(mk()), b.update_with_detections(mk())
+            assert np.array_equal(o1.tracker_id, o2.tracker_id) and np.array_equal(o1.xyxy, o2.xyxy), (seed, frames)
+            frames += 1
+    assert frames == 1600

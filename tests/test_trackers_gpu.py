@@ -88,7 +88,7 @@ def test_yolo_trackers_api_and_parity():
     yolo.predict([cv2.cvtColor(f, cv2.COLOR_BGR2RGB) for f in fr[:B]], conf=0.5, iou=0.7, imgsz=640, classes=[0])
     got = pt.detect_sample(fr[:B])
     reps = parity.check_batch(net, yolo.last_preprocessed, got, 0.5, 0.7, [0], 300, (H, W), tag="[players tracker]")
-    parity.assert_reports(reps, "players tracker", min_sure_frac=0.2)
+    parity.assert_reports(reps, "players tracker", min_sure_frac=0.2, min_tight=0)
     assert all(p.id is not None for p in pt.results.predictions[0])
     # court: the tracker returns 12 keypoints with reference ids (keypoints_tracker.py:214-227)
     k0 = kt.results.predictions[0]
