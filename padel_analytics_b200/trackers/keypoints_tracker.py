@@ -1,7 +1,7 @@
 """KeypointsTracker (court, 12 keypoints) on the B200 engine — API of
-/root/reference/trackers/keypoints_tracker/keypoints_tracker.py (:18-315); model_type="yolo" and the
-fixed-keypoints short-circuit are supported, the torchvision ResNet50 regressor (:158-167, :276-312) is not
-(its ImageNet weights cannot even be constructed offline)."""
+/root/reference/trackers/keypoints_tracker/keypoints_tracker.py (:18-315): model_type="yolo" (YOLOv8-pose, predict_sample),
+model_type="resnet" (torchvision ResNet50 regressor :158-167, predict_frames :276-312, input pipeline
+keypoints_tracker/iterable.py:10-41) and the fixed-keypoints short-circuit."""
 from __future__ import annotations
 
 from pathlib import Path
@@ -81,7 +81,14 @@ class KeypointsTracker(Tracker):
         if model_type == "yolo":
             self.model = YoloEngine(model_path, max_batch=batch_size) if model_path is not None else None
         elif model_type == "resnet":
-            raise NotImplementedError("model_type='resnet' is outside the B200 hot path (see module docstring)")
+            # reference: models.resnet50(pretrained=True) with fc -> 24, then load_state_dict(torch.load(model_path))
+            # (:158-166); the checkpoint (torchvision key names) is all that is needed here
+            import torch
+
+            from ..engine.resnet_engine import ResNet50Engine
+
+            sd = model_path if isinstance(model_path, dict) else torch.load(model_path, map_location="cpu")
+            self.model = ResNet50Engine(sd, max_batch=batch_size)
         else:
             raise ValueError("Unknown model type")
         self.fixed_keypoints_detection = fixed_keypoints_detection
@@ -139,4 +146,17 @@ class KeypointsTracker(Tracker):
     def predict_frames(self, frame_generator, **kwargs):
         if self.fixed_keypoints_detection is not None:
             return [self.fixed_keypoints_detection for _ in frame_generator]
-        raise NoPredictFrames()
+        if self.model_type == "yolo":
+            raise NoPredictFrames()
+        # ResNet50 regressor (:276-312): batches of frames -> sigmoid outputs (n, 12, 2) in [0,1]^2 -> frame pixels;
+        # keypoint ids are the output order (no points_mapper on this branch)
+        from .tracker import sampler
+
+        out = []
+        for chunk in sampler(frame_generator, self.batch_size):
+            h_frame, w_frame = chunk[0].shape[:2]
+            p = self.model.predict_frames(chunk).reshape(len(chunk), self.NUMBER_KEYPOINTS, 2)
+            for det in p:
+                out.append(Keypoints([Keypoint(i, (float(k[0] * w_frame), float(k[1] * h_frame)))
+                                      for i, k in enumerate(det)]))
+        return out

@@ -189,6 +189,23 @@ def yolo_glue_golden():
                                                 for pl in p.players], dtype=np.float64).reshape(-1, 7)
         finally:
             rpt.sv = sys.modules["supervision"]
+    # --- KeypointsTracker(model_type="resnet") (keypoints_tracker.py:158-167,276-312): torchvision's resnet50 is
+    # installed, only the `pretrained=True` download must be avoided (the state dict is loaded over it anyway)
+    import torchvision
+    from oracle import resnet as OR
+
+    with tempfile.TemporaryDirectory() as td:
+        rpath = str(Path(td) / "resnet.pt")
+        torch.save(OR.make_resnet50_court(), rpath)
+        orig_r50 = rkt.models.resnet50
+        rkt.models.resnet50 = lambda pretrained=True: orig_r50(weights=None)
+        try:
+            kt = rkt.KeypointsTracker(rpath, batch_size=2, model_type="resnet")
+            preds = kt.predict_frames(iter(frames))
+        finally:
+            rkt.models.resnet50 = orig_r50
+        out["resnet"] = np.array([[k.xy for k in sorted(p.keypoints, key=lambda k: k.id)] for p in preds], dtype=np.float64)
+        assert out["resnet"].shape == (len(frames), 12, 2)
     np.savez_compressed(OUT / "yolo_glue_ref.npz", **out)
     print("yolo_glue_ref:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 

@@ -193,3 +193,44 @@ def test_yolo_engine_predict_is_a_drop_in_for_ultralytics_predict(kind, src):
     parity.assert_reports(reps, f"predict/{kind}", min_sure_frac=0.0, min_tight=0)
     assert sum(r.n_ours for r in reps) > 0
     assert eng.predict([], **kw) == []
+
+
+def test_resnet50_court_regressor_matches_torchvision_oracle():
+    """KeypointsTracker(model_type="resnet") (keypoints_tracker.py:158-167,276-312): the torchvision ResNet50 on the
+    B200 kernels vs torchvision itself on the CPU through the reference's input pipeline (iterable.py:10-41).
+    Pre-processing is bit-exact (Pillow bilinear); the network output is compared in frame pixels."""
+    from oracle import resnet as OR
+    from padel_analytics_b200.engine.resnet_engine import ResNet50Engine
+    from padel_analytics_b200.trackers import KeypointsTracker
+
+    sd = OR.make_resnet50_court()
+    net = OR.load(sd)
+    B = 3
+    frames = synth.make_frames(5, 1080, 1920, start=5)
+    fr = [f.numpy() for f in frames]
+    eng = ResNet50Engine(sd, max_batch=B)
+    got = eng.predict_frames(fr[:B]).reshape(B, 12, 2) * np.array([1920, 1080])
+    # 1) the network input equals the reference's transforms output rounded to fp16
+    xin = OR.preprocess(fr[:B])
+    x_eng = eng.x_in[:B, ..., :3].cpu().float().permute(0, 3, 1, 2)
+    assert torch.equal(x_eng, xin.half().float())
+    # 2) keypoints
+    exp = OR.predict(net, fr[:B])
+    err = np.linalg.norm(got - exp, axis=-1)
+    print("resnet50 court regressor: keypoint error (frame px) max", err.max(), "mean", err.mean())
+    assert err.max() < 1.0, err.max()  # measured ~0.2 px; 11-bit-mantissa storage through 53 layers
+    # 3) the nn.Module-style call of the reference (model(batch) -> Sigmoid, :296-297)
+    with torch.no_grad():
+        p = torch.sigmoid(eng(xin.cuda())).cpu().numpy().reshape(B, 12, 2) * np.array([1920, 1080])
+    assert np.abs(p - got).max() < 0.05
+    # 4) the tracker: 5 frames in batches of 3 (last one partial), ids = output order, JSON round trip
+    kt = KeypointsTracker(sd, batch_size=B, model_type="resnet")
+    res = kt.predict_and_update(iter(fr)).predictions
+    assert len(res) == 5 and [k.id for k in res[0].keypoints] == list(range(12))
+    full = OR.predict(net, fr)
+    for n in range(5):
+        xy = np.array([k.xy for k in res[n].keypoints])
+        assert np.linalg.norm(xy - full[n], axis=-1).max() < 1.0
+    import json
+
+    json.dumps([o.serialize() for o in res])

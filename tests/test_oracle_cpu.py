@@ -179,3 +179,15 @@ def test_tracker_glue_reproduces_reference_golden():
         arr = np.array([[*pl.xyxy, pl.confidence, pl.class_id, -1 if pl.id is None else pl.id] for pl in p.players],
                        dtype=np.float64).reshape(-1, 7)
         assert np.array_equal(arr, g[f"players_{i}"]), f"players frame {i}"
+
+
+def test_resnet_oracle_reproduces_reference_golden():
+    """oracle/resnet.py (pipeline restatement around torchvision's resnet50) vs the golden produced by the unmodified
+    reference KeypointsTracker(model_type="resnet").predict_frames on the rally.mp4 crops."""
+    from fixtures import GOLDEN, rally_frames
+    from oracle import resnet as OR
+
+    g = np.load(GOLDEN / "yolo_glue_ref.npz")
+    got = OR.predict(OR.load(OR.make_resnet50_court()), rally_frames())
+    # the reference multiplies float32 sigmoid outputs by the integer frame size (float32 products)
+    assert np.abs(got - g["resnet"]).max() < 1e-3
