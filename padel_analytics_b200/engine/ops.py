@@ -193,10 +193,13 @@ class Program:
             L.check(L.lib().pb_program_run_range(self._h, first, last, L.stream_ptr()))
 
 
-def time_program_ops(prog: Program, repeats: int = 3):
-    """Per-op device time (ms) with CUDA events recorded on the launch stream between consecutive ops."""
+def time_program_ops(prog: Program, repeats: int = 5):
+    """Per-op device time (ms) with CUDA events recorded on the launch stream between consecutive ops: the MEDIAN of
+    `repeats` passes (a best-of-n would flatter the roofline numerator)."""
+    import statistics
+
     n = prog.num_ops
-    best = [float("inf")] * n
+    samples = [[] for _ in range(n)]
     for _ in range(repeats):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         ev[0].record()
@@ -205,5 +208,5 @@ def time_program_ops(prog: Program, repeats: int = 3):
             ev[i + 1].record()
         torch.cuda.synchronize()
         for i in range(n):
-            best[i] = min(best[i], ev[i].elapsed_time(ev[i + 1]))
-    return best
+            samples[i].append(ev[i].elapsed_time(ev[i + 1]))
+    return [statistics.median(s) for s in samples]

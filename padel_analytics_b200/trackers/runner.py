@@ -259,7 +259,10 @@ class TrackingRunner:
 
         med = None
         if rank == 0:
-            frames = list(src(0, min(total, tracker.median_max_sample_num)))
+            m = min(total, tracker.median_max_sample_num)
+            frames = list(src(0, m))
+            if frames and isinstance(frames[0], torch.Tensor) and frames[0].dim() == 4:  # batched source
+                frames = torch.cat([f.to("cuda") for f in frames])[:m]
             med = median_background(frames)
         if dist_on:
             dev = _comm_device()
@@ -289,15 +292,21 @@ class TrackingRunner:
         parts = {n: [] for n in model}
         hw = None
         if first is not None:
-            hw = tuple(first.shape[:2])
+            # a frame source may yield single HWC frames (video decode) or ready uint8 (n,H,W,3) batches, n <= B
+            # (pinned host or device tensors: no per-frame host copy)
+            batched = isinstance(first, torch.Tensor) and first.dim() == 4
+            hw = tuple(first.shape[1:3]) if batched else tuple(first.shape[:2])
             single = not dist_on
             fp = FusedPass(model, hw, B, total_frames=total, first_frame=flo, emit_range=(lo, hi), raw=not single,
                            median=median)
-            pinned = [torch.empty((B,) + hw + (3,), dtype=torch.uint8).pin_memory() for _ in range(3)]
+            pinned = None if batched else [torch.empty((B,) + hw + (3,), dtype=torch.uint8).pin_memory() for _ in range(3)]
 
             def batches():
                 import itertools
 
+                if batched:
+                    yield from itertools.chain([first], it)
+                    return
                 chunk_it = sampler(itertools.chain([first], it), B)
                 for i, chunk in enumerate(chunk_it):
                     buf = pinned[i % 3]
