@@ -1,4 +1,5 @@
 // C-ABI surface of libpadel_b200.so: error reporting, programs (op lists), one-shot conv launches.
+#include <map>
 #include <memory>
 #include <mutex>
 #include <vector>
@@ -29,6 +30,22 @@ int num_sms() {
       sms = 148;
   });
   return sms;
+}
+
+int ensure_dynamic_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> configured;
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& have = configured[{dev, func}];
+  if (bytes > have) {
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+  }
+  return e;
 }
 
 bool pdl_enabled() {

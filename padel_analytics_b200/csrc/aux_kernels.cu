@@ -206,11 +206,7 @@ int launch_pointwise_head(const void* in, int N, int H, int W, int C, const floa
   const size_t wfloats = (size_t)((n_out * C + n_out + 3) & ~3);
   const size_t smem = wfloats * sizeof(float) + (size_t)kHeadPix * (C / 8 + 1) * sizeof(uint4);
   PB_CHECK(smem <= 96 * 1024, "pointwise_head: C = %d too wide for the staged tile", C);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    PB_CUDA(cudaFuncSetAttribute(pointwise_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(pointwise_head_kernel), smem));
   long blocks = (npix + kHeadPix - 1) / kHeadPix;
   const long cap = (long)num_sms() * 5;
   if (blocks > cap) blocks = cap;
@@ -225,11 +221,7 @@ int launch_sppf_pool(void* buf, int N, int H, int W, int C, int c, cudaStream_t 
   PB_CHECK(c % 8 == 0 && C >= 4 * c && C % 8 == 0, "sppf: bad channel layout");
   const size_t smem = (size_t)2 * H * W * sizeof(uint4);
   PB_CHECK(smem <= 200 * 1024, "sppf: %dx%d plane does not fit in shared memory", H, W);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    PB_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(sppf_pool_kernel), smem));
   PB_CUDA(launch_pdl(sppf_pool_kernel, dim3(N * (c / 8)), dim3(256), smem, s, 1, reinterpret_cast<__half*>(buf), N, H, W,
                      C, c / 8));
   count_launch();

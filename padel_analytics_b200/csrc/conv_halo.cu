@@ -742,18 +742,7 @@ int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
   const ConvKParams& kp = plan->kp;
   HaloKernelFn fn = kp.pair ? halo_kernel_for<true>(kp.hs_S, kp.KB / 16) : halo_kernel_for<false>(kp.hs_S, kp.KB / 16);
   PB_CHECK(fn != nullptr, "conv(halo): no kernel instantiation for S=%d, k-steps=%d", kp.hs_S, kp.KB / 16);
-  {
-    static std::mutex mu;
-    static std::vector<const void*> configured;
-    std::lock_guard<std::mutex> lk(mu);
-    bool seen = false;
-    for (const void* p : configured) seen = seen || p == reinterpret_cast<const void*>(fn);
-    if (!seen) {
-      PB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   227 * 1024));
-      configured.push_back(reinterpret_cast<const void*>(fn));
-    }
-  }
+  PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
   cudaError_t le = launch_pdl(fn, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, kp.pair ? 2 : 1,
                               plan->tmap_a, plan->tmap_w, plan->kp);
   PB_CHECK(le == cudaSuccess,

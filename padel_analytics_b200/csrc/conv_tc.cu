@@ -532,12 +532,7 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
 
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
   if (plan->variant == 1) return conv_halo_launch(plan, stream);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  PB_CHECK(attr_err == cudaSuccess, "conv: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
+  PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(conv_tc_kernel), 227 * 1024));
   PB_CUDA(launch_pdl(conv_tc_kernel, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, 1, plan->tmap_a,
                      plan->tmap_w, plan->kp));
   count_launch();

@@ -119,11 +119,7 @@ extern "C" int pb_inpaintnet_forward(const float* coor, const float* mask, int N
     off += chans[i][1];
   }
   const size_t smem = (size_t)(3 + 32 + 64 + 128 + 256 + 256 + 128 + 64 + 32 + 2) * L * sizeof(float);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    PB_CUDA(cudaFuncSetAttribute(inpaintnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(inpaintnet_kernel), smem));
   inpaintnet_kernel<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(coor, mask, weights, p, out);
   PB_CUDA(cudaGetLastError());
   count_launch();

@@ -18,6 +18,9 @@ void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int num_sms();
+// Raise a kernel's dynamic shared-memory limit to at least `bytes` on the CURRENT device (the attribute is per device
+// and per function; remembered per (device, function) so the driver call happens once).  Returns a cudaError_t.
+int ensure_dynamic_smem(const void* func, size_t bytes);
 // Programmatic dependent launch for the kernels of a program (PADEL_B200_PDL=0 disables; default on)
 bool pdl_enabled();
 

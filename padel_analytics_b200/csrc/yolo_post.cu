@@ -246,7 +246,7 @@ int pb_yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count
   PB_CHECK(P <= 32768, "yolo_nms: candidate capacity %d > 32768 (ultralytics max_nms is 30000)", cap);
   PB_CHECK(cap <= kNmsSmemCap || scratch != nullptr, "yolo_nms: cap %d > %d needs a scratch buffer", cap, kNmsSmemCap);
   const size_t smem = (size_t)(P < kNmsSmemCap ? P : kNmsSmemCap) * (8 + 16 + 4 + 1);
-  PB_CUDA(cudaFuncSetAttribute(yolo_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(yolo_nms_kernel), smem));
   yolo_nms_kernel<<<B, 1024, smem, static_cast<cudaStream_t>(stream)>>>(
       cand, cand_anchor, cand_count, cap, P, rowlen, iou, max_det, out, out_count, static_cast<uint8_t*>(scratch));
   PB_CUDA(cudaGetLastError());

@@ -312,13 +312,26 @@ class BallTracker(Tracker):
         return res
 
     def inpaint_xyv(self, xyv: dict, total_frames: int) -> dict:
-        """Apply the InpaintNet stage to a complete {frame: (x, y, vis)} trajectory (no-op without an inpainting model
-        or when frames are missing); used by predict_frames and by the sharded runner on rank 0."""
-        if getattr(self, "inpaintnet", None) is None or len(xyv) != total_frames:
+        """Apply the InpaintNet stage to a {frame: (x, y, vis)} trajectory (no-op without an inpainting model); used by
+        predict_frames and by the sharded runner on rank 0.  The reference feeds whatever TrackNet produced (frames
+        0..T'-1) to the inpainting stage; if fewer frames than announced arrived (CAP_PROP_FRAME_COUNT often
+        over-reports: the tail flush never fires and the last 7 frames are missing) the stage runs over the contiguous
+        range that is present, with a warning, instead of being skipped."""
+        if getattr(self, "inpaintnet", None) is None or not xyv:
             return xyv
-        # the reference feeds every TrackNet prediction (frames 0..T-1) to the inpainting stage
         order = sorted(xyv)
-        return self._inpaint_stage([xyv[n][0] for n in order], [xyv[n][1] for n in order], [xyv[n][2] for n in order])
+        lo, hi = order[0], order[-1]
+        if len(order) != hi - lo + 1:
+            print(f"{self}: TrackNet results are not a contiguous frame range ({len(order)} frames in [{lo}, {hi}]); "
+                  f"InpaintNet stage skipped")
+            return xyv
+        if len(order) != total_frames:
+            print(f"{self}: {len(order)} of {total_frames} announced frames have TrackNet results; "
+                  f"inpainting frames {lo}..{hi}")
+        res = self._inpaint_stage([xyv[n][0] for n in order], [xyv[n][1] for n in order], [xyv[n][2] for n in order])
+        out = dict(xyv)
+        out.update({lo + k: v for k, v in res.items()})
+        return out
 
     def predict_frames(self, frame_generator: Iterable[np.ndarray], total_frames: int, **kwargs) -> list[Ball]:
         xyv = self.inpaint_xyv(self.track_xyv(frame_generator, total_frames), total_frames)

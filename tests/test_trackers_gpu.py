@@ -297,3 +297,35 @@ def test_inpaintnet_kernel_and_stage_match_oracle():
     assert dx <= 1 and dy <= 1, (dx, dy)  # fp32 kernel vs fp32 CPU convs: integer truncation may move one pixel
     exact = sum(1 for n in range(len(X)) if (res[n][0], res[n][1]) == (X[n], Y[n]))
     assert exact >= len(X) - 3
+
+
+def test_config0_players_tracker_batch1_on_real_720p_frames():
+    """BASELINE.json configs[0]: PlayerTracker only (YOLOv8n-detect), 720p frames of the example clip, batch_size = 1,
+    through TrackingRunner.run() (one tracker -> the reference's plain per-tracker loop).  Real video content
+    (the committed rally.mp4 frame, shifted to fake motion); detections vs the CPU oracle under the protocol, ids
+    from the ByteTrack stage, JSON round trip."""
+    import parity
+    from fixtures import GOLDEN, glue_ckpt
+
+    base = cv2.imread(str(GOLDEN / "rally" / "rally_f00_720p.jpg"))
+    assert base.shape == (720, 1280, 3)
+    fr = [np.ascontiguousarray(np.roll(base, 6 * i, axis=1)) for i in range(6)]
+    Hh, Ww = 720, 1280
+    ck = glue_ckpt("detect")
+    poly = sv.PolygonZone(np.array([[0, 0], [Ww, 0], [Ww, Hh], [0, Hh]]), frame_resolution_wh=(Ww, Hh))
+    pt = PlayerTracker(ck, poly, batch_size=1)
+    run = TrackingRunner([pt], video_info=sv.VideoInfo(width=Ww, height=Hh, fps=25.0, total_frames=len(fr)))
+    tm = run.run(frame_source=lambda lo, hi: iter(fr[lo:hi]), total_frames=len(fr))
+    assert set(tm) == {"players_tracker"} and len(pt.results) == len(fr)
+    json.dumps([o.serialize() for o in pt.results.predictions])
+    ids = [p.id for o in pt.results.predictions for p in o]
+    assert all(i is not None and i >= 1 for i in ids)
+    net = OW.load_yolo(ck)
+    yolo = OY.YOLO(net)
+    yolo.predict([cv2.cvtColor(f, cv2.COLOR_BGR2RGB) for f in fr[:2]], conf=0.5, iou=0.7, imgsz=640, classes=[0])
+    got = []
+    for f in fr[:2]:  # batch_size = 1
+        got += pt.detect_sample([f])
+    reps = parity.check_batch(net, yolo.last_preprocessed, got, 0.5, 0.7, [0], 300, (Hh, Ww), tag="[configs[0] 720p]")
+    parity.assert_reports(reps, "configs[0] 720p", min_sure_frac=0.0, min_tight=0)
+    assert sum(r.n_ours for r in reps) > 0
