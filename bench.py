@@ -353,15 +353,17 @@ def run_strong(args, rank, world, local, dev):
             yield pool[i % NB][:n]
             pos, i = pos + n, i + 1
 
+    tr, _ = build_trackers(B, (H, W), ckpts, dev, which)  # engines are built once, like loading the models once
+    run = TrackingRunner(list(tr.values()), video_info=sv.VideoInfo(width=W, height=H, fps=30.0, total_frames=N))
+
     def one_pass():
-        tr, _ = build_trackers(B, (H, W), ckpts, dev, which)
-        run = TrackingRunner(list(tr.values()), video_info=sv.VideoInfo(width=W, height=H, fps=30.0, total_frames=N))
+        run.restart()  # empty results, ByteTrack reset: run() would skip trackers that already hold predictions
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         l0 = L.lib().pb_launch_count()
         t0 = time.perf_counter()
-        tm = run.run(frame_source=source, total_frames=N)
+        tm = dict(run.run(frame_source=source, total_frames=N))
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         if world > 1:

@@ -251,7 +251,7 @@ def non_max_suppression(pred, conf_thres, iou_thres, classes, max_det, nc, max_n
     xc = pred[:, 4:mi].amax(1) > conf_thres
     pred = pred.transpose(-1, -2).clone()
     pred[..., :4] = xywh2xyxy(pred[..., :4])
-    out = [torch.zeros((0, 6 + pred.shape[-1] - mi))] * bs
+    out = [torch.zeros((0, 6 + pred.shape[-1] - mi), device=pred.device)] * bs
     for xi, x in enumerate(pred):
         x = x[xc[xi]]
         if not x.shape[0]:
@@ -260,7 +260,7 @@ def non_max_suppression(pred, conf_thres, iou_thres, classes, max_det, nc, max_n
         conf, j = cls.max(1, keepdim=True)
         x = torch.cat((box, conf, j.float(), mask), 1)[conf.view(-1) > conf_thres]
         if classes is not None:
-            x = x[(x[:, 5:6] == torch.tensor(classes, dtype=x.dtype)).any(1)]
+            x = x[(x[:, 5:6] == torch.tensor(classes, dtype=x.dtype, device=x.device)).any(1)]
         n = x.shape[0]
         if not n:
             continue

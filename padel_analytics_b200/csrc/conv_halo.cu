@@ -73,6 +73,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // bring-up timeline (libpadel_b200_debug.so only: kp.dbg is NULL in the product build): GPU-wide nanosecond stamps of
+  // the first and the last CTA -- entry, after griddepcontrol.wait, exit -- to see how consecutive layers overlap
+  const bool gdbg = kp.dbg != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+  long long* gslot = kp.dbg + (3 * 64 + (blockIdx.x == 0 ? 0 : 1)) * 4;
+  if (gdbg) gslot[0] = (long long)globaltimer_ns();
   constexpr int S = kS;
   const int G = kp.hs_G;
   const uint32_t row_bytes = (uint32_t)kp.KB * 2u;       // weight rows (and activation rows unless stride 2)
@@ -121,6 +126,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // producer (warp 6) reads constants only and starts fetching while the previous kernel is still running.
   griddep_launch_dependents();
   if (warp != 6) griddep_wait();
+  if (gdbg) gslot[1] = (long long)globaltimer_ns();
 
   if (warp == 0) {
     // ===================== halo producer: one TMA box per (tile, channel block) =====================
@@ -359,6 +365,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (gdbg) gslot[2] = (long long)globaltimer_ns();
   if (pair) cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();

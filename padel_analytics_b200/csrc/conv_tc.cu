@@ -59,6 +59,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // bring-up timeline (libpadel_b200_debug.so only: kp.dbg is NULL in the product build): GPU-wide nanosecond stamps of
+  // the first and the last CTA -- entry, after griddepcontrol.wait, exit -- to see how consecutive layers overlap
+  const bool gdbg = kp.dbg != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+  long long* gslot = kp.dbg + (3 * 64 + (blockIdx.x == 0 ? 0 : 1)) * 4;
+  if (gdbg) gslot[0] = (long long)globaltimer_ns();
   const int k_iters = kp.taps * kp.kblocks;
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_a);
@@ -87,6 +92,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // producer (warp 6) reads constants only and starts fetching while the previous kernel is still running.
   griddep_launch_dependents();
   if (warp != 6) griddep_wait();
+  if (gdbg) gslot[1] = (long long)globaltimer_ns();
 
   if (warp == 0) {
     // ============================== TMA producer: activations ==============================
@@ -286,6 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (gdbg) gslot[2] = (long long)globaltimer_ns();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)kp.tmem_cols);

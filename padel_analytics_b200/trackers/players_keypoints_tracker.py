@@ -2,7 +2,6 @@
 /root/reference/trackers/players_keypoints_tracker/players_keypoints_tracker.py (:15-327)."""
 from __future__ import annotations
 
-from dataclasses import dataclass
 from pathlib import Path
 from typing import Iterable, Optional, Type
 
@@ -12,11 +11,21 @@ from ..engine.yolo_engine import YoloEngine
 from .tracker import NoPredictFrames, Object, Tracker
 
 
-@dataclass
 class PlayerKeypoint:
-    id: int
-    name: str
-    xy: tuple[float, float]
+    """One named keypoint of one player (players_keypoints_tracker.py:15-57).  A plain __slots__ class: a frame holds
+    ~200 of them and rank 0 builds them for every frame of every shard."""
+    __slots__ = ("id", "name", "xy")
+
+    def __init__(self, id: int, name: str, xy: tuple[float, float]):
+        self.id = id
+        self.name = name
+        self.xy = xy
+
+    def __eq__(self, other):
+        return isinstance(other, PlayerKeypoint) and (self.id, self.name, self.xy) == (other.id, other.name, other.xy)
+
+    def __repr__(self):
+        return f"PlayerKeypoint(id={self.id}, name={self.name!r}, xy={self.xy})"
 
     def asint(self):
         return tuple(int(v) for v in self.xy)
@@ -46,7 +55,13 @@ class PlayerKeypoints:
 
     def __init__(self, player_keypoints: list[PlayerKeypoint]):
         self.player_keypoints = player_keypoints
-        self.keypoints_by_name = {k.name: k for k in player_keypoints}
+        self._by_name = None
+
+    @property
+    def keypoints_by_name(self) -> dict:
+        if self._by_name is None:
+            self._by_name = {k.name: k for k in self.player_keypoints}
+        return self._by_name
 
     @classmethod
     def from_json(cls, x: dict):
@@ -77,19 +92,41 @@ class PlayerKeypoints:
 
 
 class PlayersKeypoints(Object):
-    def __init__(self, players_keypoints: list[PlayerKeypoints]) -> None:
+    """All players' keypoints of one frame (players_keypoints_tracker.py:165-205).  Array-backed: the tracker hands in
+    the frame's (players, 13, 2) coordinates and the PlayerKeypoints / PlayerKeypoint objects (~200 per frame) are only
+    materialised when `players_keypoints` is read -- rank 0 assembles every frame of every shard, and a consumer that
+    only serialises or counts never pays for the objects."""
+
+    def __init__(self, players_keypoints: list[PlayerKeypoints] | None = None, _xy: list | None = None) -> None:
         super().__init__()
-        self.players_keypoints = players_keypoints
+        self._list = players_keypoints
+        self._xy = _xy  # (players, 13, 2) float64 ndarray when built by the tracker
+
+    @classmethod
+    def from_xy(cls, xy: list) -> "PlayersKeypoints":
+        return cls(None, _xy=xy)
+
+    @property
+    def players_keypoints(self) -> list[PlayerKeypoints]:
+        if self._list is None:
+            names = PlayerKeypoints.KEYPOINTS_NAMES
+            self._list = [PlayerKeypoints([PlayerKeypoint(i, names[i], (x, y)) for i, (x, y) in enumerate(det)])
+                          for det in self._xy.tolist()]
+        return self._list
 
     @classmethod
     def from_json(cls, x) -> "PlayersKeypoints":
         return cls([PlayerKeypoints.from_json(p) for p in x])
 
     def serialize(self) -> list[dict]:
-        return [p.serialize() for p in self.players_keypoints]
+        if self._list is None:  # straight from the coordinates, same JSON as the objects would give
+            names = PlayerKeypoints.KEYPOINTS_NAMES
+            return [{"player_keypoints": [{"id": i, "name": names[i], "xy": (x, y)} for i, (x, y) in enumerate(det)]}
+                    for det in self._xy.tolist()]
+        return [p.serialize() for p in self._list]
 
     def __len__(self):
-        return len(self.players_keypoints)
+        return len(self._xy) if self._list is None else len(self._list)
 
     def __iter__(self):
         return iter(self.players_keypoints)
@@ -151,9 +188,7 @@ class PlayerKeypointsTracker(Tracker):
         for result in results:
             # float32 -> Python float (exact) * Python float ratio, as `keypoint[0].item() * ratio_x` does (:306-309)
             xy = result.keypoints.xy.numpy().astype(np.float64) * np.array([ratio_x, ratio_y])
-            players = [PlayerKeypoints([PlayerKeypoint(id=i, name=names[i], xy=(x, y)) for i, (x, y) in enumerate(det)])
-                       for det in xy.tolist()]
-            out.append(PlayersKeypoints(players))
+            out.append(PlayersKeypoints.from_xy(xy.reshape(-1, len(names), 2)))
         return out
 
     def predict_sample(self, sample: Iterable[np.ndarray], **kwargs) -> list[PlayersKeypoints]:

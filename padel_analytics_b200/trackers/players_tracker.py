@@ -13,14 +13,38 @@ from .tracker import NoPredictFrames, Object, Tracker
 
 
 class Player:
+    """players_tracker.py:14-197.  Built either from a one-row `Detections` (the reference's constructor) or, on the
+    fast path, straight from the row's values (`from_row`): slicing a Detections per player costs more than the
+    ByteTrack update of the whole frame, and rank 0 does it for every frame of every shard."""
+
     def __init__(self, detection, projection: Optional[tuple[int, int]] = None):
-        self.detection = detection
+        self._detection = detection
         self.projection = projection
         self.xyxy = detection.xyxy[0]
         tid = detection.tracker_id
         self.id = int(tid[0]) if tid is not None and len(tid) else None
         self.class_id = int(detection.class_id[0])
         self.confidence = float(detection.confidence[0])
+
+    @classmethod
+    def from_row(cls, xyxy, tracker_id, class_id, confidence, projection=None) -> "Player":
+        p = cls.__new__(cls)
+        p._detection = None
+        p.projection = projection
+        p.xyxy = xyxy
+        p.id = None if tracker_id is None else int(tracker_id)
+        p.class_id = int(class_id)
+        p.confidence = float(confidence)
+        return p
+
+    @property
+    def detection(self):
+        if self._detection is None:
+            self._detection = sv.Detections(xyxy=np.asarray(self.xyxy).reshape(1, 4),
+                                            confidence=np.array([self.confidence], dtype=np.float32),
+                                            class_id=np.array([self.class_id]),
+                                            tracker_id=None if self.id is None else np.array([self.id]))
+        return self._detection
 
     @property
     def top_left(self):
@@ -68,9 +92,26 @@ class Player:
 
 
 class Players(Object):
-    def __init__(self, players: list[Player]):
+    """All tracked players of one frame (players_tracker.py:199-263).  Array-backed like PlayersKeypoints: the tracker
+    hands in the frame's rows (xyxy, id, class, confidence) and the Player objects are materialised when `players` is
+    read."""
+
+    def __init__(self, players: list[Player] | None = None, _rows=None):
         super().__init__()
-        self.players = players
+        self._list = players
+        self._rows = _rows  # (xyxy (n,4) float32, ids (n,) int | None, class_id (n,), confidence (n,))
+
+    @classmethod
+    def from_rows(cls, xyxy, ids, class_id, confidence) -> "Players":
+        return cls(None, _rows=(xyxy, ids, class_id, confidence))
+
+    @property
+    def players(self) -> list[Player]:
+        if self._list is None:
+            xyxy, ids, cid, conf = self._rows
+            self._list = [Player.from_row(xyxy[i], None if ids is None else ids[i], cid[i], conf[i])
+                          for i in range(len(xyxy))]
+        return self._list
 
     @classmethod
     def from_json(cls, x: list[dict]) -> "Players":
@@ -80,7 +121,7 @@ class Players(Object):
         return [p.serialize() for p in self.players]
 
     def __len__(self):
-        return len(self.players)
+        return len(self._rows[0]) if self._list is None else len(self._list)
 
     def __iter__(self):
         return iter(self.players)
@@ -148,7 +189,7 @@ class PlayerTracker(Tracker):
             if self.polygon_zone is not None:
                 det = det[self.polygon_zone.trigger(det)]
             det = self.byte_track.update_with_detections(detections=det)
-            out.append(Players([Player(detection=det[i]) for i in range(len(det))]))
+            out.append(Players.from_rows(det.xyxy, det.tracker_id, det.class_id, det.confidence))
         return out
 
     def predict_sample(self, sample: Iterable[np.ndarray], **kwargs) -> list[Players]:

@@ -117,13 +117,18 @@ def test_yolo_trackers_api_and_parity():
     assert nsure >= 3, "vacuous"
 
 
-def _four_trackers(B, med=None, **ball_kw):
+def _four_ckpts():
+    return {"detect": OW.make_yolo("detect"), "pose13": OW.make_yolo("pose13", cls_mean=-5.5),
+            "court12": OW.make_yolo("court12"), "tracknet": OW.make_tracknet()}
+
+
+def _four_trackers(B, med=None, ckpts=None, **ball_kw):
+    ck = ckpts or _four_ckpts()
     poly = sv.PolygonZone(np.array([[0, 0], [W - 1, 0], [W - 1, H - 1], [0, H - 1]]), frame_resolution_wh=(W, H))
-    return [PlayerTracker(OW.make_yolo("detect"), poly, batch_size=B),
-            PlayerKeypointsTracker(OW.make_yolo("pose13", cls_mean=-5.5), 1280, batch_size=B, load_path=None,
-                                   save_path=None),
-            KeypointsTracker(OW.make_yolo("court12"), batch_size=B, model_type="yolo"),
-            BallTracker(OW.make_tracknet(), None, batch_size=B, median=med, **ball_kw)]
+    return [PlayerTracker(ck["detect"], poly, batch_size=B),
+            PlayerKeypointsTracker(ck["pose13"], 1280, batch_size=B, load_path=None, save_path=None),
+            KeypointsTracker(ck["court12"], batch_size=B, model_type="yolo"),
+            BallTracker(ck["tracknet"], None, batch_size=B, median=med, **ball_kw)]
 
 
 def _dump(trackers):
@@ -194,6 +199,10 @@ def test_runner_sharded_over_nccl_equals_unsharded(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = Path(__file__).resolve().parents[1]
+    # one set of checkpoints for every process: the seeded factory standardises the heads with CPU convolutions whose
+    # last bits depend on the thread count (torchrun sets OMP_NUM_THREADS=1), and the comparison below is exact
+    cks = _four_ckpts()
+    torch.save(cks, tmp_path / "ckpts.pt")
     script = tmp_path / "nccl2.py"
     script.write_text(f"""
 import sys, json, os
@@ -206,7 +215,7 @@ from padel_analytics_b200.trackers import TrackingRunner
 from test_trackers_gpu import _four_trackers, _dump, _vi, H, W
 T, B = 37, 4
 fr = [f.numpy() for f in synth.make_frames(T, H, W, start=7)]
-tr = _four_trackers(B, None, median_max_sample_num=11)
+tr = _four_trackers(B, None, ckpts=torch.load({str(tmp_path / 'ckpts.pt')!r}, weights_only=False), median_max_sample_num=11)
 run = TrackingRunner(tr, video_info=_vi(T))
 t = run.run(frame_source=lambda lo, hi: iter(fr[lo:hi]), total_frames=T)
 if dist.get_rank() == 0:
@@ -222,12 +231,16 @@ dist.destroy_process_group()
     print(r.stdout[-400:])
     T, B = 37, 4
     fr = [f.numpy() for f in synth.make_frames(T, H, W, start=7)]
-    tr = _four_trackers(B, None, median_max_sample_num=11)
+    tr = _four_trackers(B, None, ckpts=cks, median_max_sample_num=11)
     TrackingRunner(tr, video_info=_vi(T)).run(frame_source=lambda lo, hi: iter(fr[lo:hi]), total_frames=T)
     sharded = json.loads((tmp_path / "sharded.json").read_text())
     single = _dump(tr)
     for k in single:
-        assert sharded[k] == single[k], k
+        if sharded[k] != single[k]:  # say where: first differing frame and its two versions
+            a, b = json.loads(sharded[k]), json.loads(single[k])
+            n = next(i for i in range(max(len(a), len(b))) if i >= min(len(a), len(b)) or a[i] != b[i])
+            raise AssertionError(f"{k}: first difference at frame {n} of {len(a)}/{len(b)}\n sharded: "
+                                 f"{json.dumps(a[n])[:1500]}\n single : {json.dumps(b[n])[:1500]}")
 
 
 def test_fused_pass_equals_per_tracker_passes():
