@@ -384,10 +384,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 static void halo_finish_config(ConvPlan* plan) {
   ConvKParams& kp = plan->kp;
   const size_t need = (size_t)kp.a_stages * kp.a_bytes + (size_t)kp.b_stages * kp.b_bytes + sizeof(HaloSmemTail) + 1024;
-  const char* eo = getenv("PADEL_B200_CONV_OCC2");
+  const int occ_mode = conv_occ_mode();
   const int set_cols = kp.hs_S * kp.acc_cols;
-  const bool occ2 = !kp.pair && (!eo || atoi(eo) != 0) && need <= 110 * 1024 && set_cols * 2 <= 256 &&
-                    kp.total_tiles > num_sms();
+  // Half-SM footprint (224 threads, <= 110 KB, 256 TMEM columns): (a) light layers with many tiles run two CTAs of the
+  // SAME kernel per SM; (b) tiny layers (at most two tiles per SM) take it so that CTAs of CONSECUTIVE kernels can be
+  // co-resident -- with programmatic dependent launch the successor then sits through its launch latency (~10 us from
+  // trigger to release, profiles/r02_chain_timeline.txt) while this kernel still computes.
+  const bool tiny = kp.total_tiles <= 2 * num_sms();
+  const bool occ2 = !kp.pair && occ_mode != 0 && need <= 110 * 1024 &&
+                    ((set_cols * 2 <= 256 && kp.total_tiles > num_sms()) || (occ_mode == 2 && tiny && set_cols <= 256));
   plan->smem_bytes = need;
   if (occ2) {
     if (kp.acc_stages * set_cols > 256) kp.acc_stages = 256 / set_cols;
@@ -575,7 +580,10 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   if (resident) {
     // the filter bank occupies kblocks fixed slots; whatever is left goes to halo buffers (up to kHaloMaxA)
     kp.b_stages = kp.kblocks;
-    const bool small = (size_t)2 * kp.a_bytes + res_total + sizeof(HaloSmemTail) + 1024 <= 108 * 1024 && S * acc_cols * 2 <= 256;
+    const bool tiny_mode = conv_occ_mode() == 2 && !kp.pair &&
+                           (long)((kp.Wo + 8 * S - 1) / (8 * S)) * ((kp.Ho + 15) / 16) * kp.N <= 2L * num_sms();
+    const bool small = (size_t)2 * kp.a_bytes + res_total + sizeof(HaloSmemTail) + 1024 <= 108 * 1024 &&
+                       (S * acc_cols * 2 <= 256 || (tiny_mode && S * acc_cols <= 256));
     const size_t budget2 = small ? (size_t)108 * 1024 - sizeof(HaloSmemTail) - 1024 : budget;
     int as = (int)((budget2 - res_total) / kp.a_bytes);
     if (as > kHaloMaxA) as = kHaloMaxA;
@@ -584,8 +592,10 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   } else {
   // light layers: size the rings for half an SM so that two CTAs can be co-resident (see halo_finish_config)
   const int min_b_small = G == 9 ? 2 : (G == 3 ? 3 : 4);
+  const bool tiny_mode = conv_occ_mode() == 2 && !kp.pair &&
+                         (long)((kp.Wo + 8 * S - 1) / (8 * S)) * ((kp.Ho + 15) / 16) * kp.N <= 2L * num_sms();
   const bool small = (size_t)2 * kp.a_bytes + (size_t)min_b_small * b_alloc + sizeof(HaloSmemTail) + 1024 <= 108 * 1024 &&
-                     S * acc_cols * 2 <= 256;
+                     (S * acc_cols * 2 <= 256 || (tiny_mode && S * acc_cols <= 256));
   const size_t budget2 = small ? (size_t)108 * 1024 - sizeof(HaloSmemTail) - 1024 : budget;
   size_t rest = budget2 - (size_t)2 * kp.a_bytes;
   if (kp.kblocks > 2 && rest > (size_t)kp.a_bytes + 4 * (size_t)b_alloc) {  // a third halo buffer when K is deep

@@ -469,9 +469,11 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
   const uint32_t stage_bytes = kp.a_bytes + kp.b_bytes;
   // Two CTAs per SM for light layers (small stages, narrow N): each gets half the shared memory and 256 TMEM
   // columns, so one CTA's TMA / epilogue latency is covered by the other's work.  PADEL_B200_CONV_OCC2=0 disables.
-  const char* eo = getenv("PADEL_B200_CONV_OCC2");
-  const bool occ2 = (!eo || atoi(eo) != 0) && (size_t)stage_bytes * 6 <= 96 * 1024 && kp.acc_cols * 2 <= 256 &&
-                    kp.total_tiles > num_sms();
+  const int occ_mode = conv_occ_mode();
+  const bool tiny = kp.total_tiles <= 2 * num_sms();  // see halo_finish_config: co-residency of consecutive kernels
+  const bool occ2 = occ_mode != 0 &&
+                    (((size_t)stage_bytes * 6 <= 96 * 1024 && kp.acc_cols * 2 <= 256 && kp.total_tiles > num_sms()) ||
+                     (occ_mode == 2 && tiny && (size_t)stage_bytes * 2 <= 96 * 1024 && kp.acc_cols <= 256));
   const size_t budget = occ2 ? 96 * 1024 : 200 * 1024;
   int stages = (int)(budget / stage_bytes);
   if (stages > kConvMaxStages) stages = kConvMaxStages;

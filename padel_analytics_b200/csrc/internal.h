@@ -91,6 +91,12 @@ inline int conv_pick_egroups(int acc_stages) {
   if (want > acc_stages) want = acc_stages;
   return want < 1 ? 1 : want;
 }
+// PADEL_B200_CONV_OCC2: 0 = never two CTAs per SM, 1 = light many-tile layers, 2 (default) = also tiny layers
+inline int conv_occ_mode() {
+  const char* e = getenv("PADEL_B200_CONV_OCC2");
+  const int m = e ? atoi(e) : 1;
+  return m < 0 || m > 2 ? 1 : m;
+}
 constexpr int kConvMaxCout = 2048;  // ResNet50 layer4 (keypoints_tracker.py:158)
 
 // Division by a launch-time constant as multiply-high + shift (dividend < 2^31): the per-tile coordinate decode of the
