@@ -40,6 +40,12 @@ extern "C" {
 #define PB_IN_NHWC 0
 #define PB_IN_STEM4 1
 #define PB_OUT_NONE 4         /* nothing stored by the conv itself (only valid with a fused head)              */
+/* secondary output of a conv whose primary output is PB_OUT_F16_NHWC (out2_mode) */
+#define PB_OUT2_NONE 0
+#define PB_OUT2_UP2 1   /* also write every pixel 2x2-replicated into a slice of a (2Ho, 2Wo) tensor: the nearest
+                           upsample of ultralytics layers 10 / 13 without a separate pass over the data            */
+#define PB_OUT2_POOL2 2 /* also write the 2x2/stride-2 max-pool into a slice of a (Ho/2, Wo/2) tensor: TrackNet's
+                           MaxPool2d after each encoder block (models.py:60,62,64); 3x3 stride-1 convs only       */
 
 const char* pb_last_error(void);
 int pb_version(void);
@@ -83,6 +89,9 @@ typedef struct pb_conv_desc {
   /* 1: out = act(conv + bias + res) -- the torchvision ResNet Bottleneck (relu(bn3(conv3) + identity), the court
    * regressor of keypoints_tracker.py:158-167); 0: out = act(conv + bias) + res.                                 */
   int res_before_act;
+  /* optional secondary output (see PB_OUT2_*): half NHWC tensor, channel stride out2_C, first channel out2_coff */
+  void* out2;
+  int out2_C, out2_coff, out2_mode;
 } pb_conv_desc;
 
 /* One-shot launches (plan + run). The *_reference variant is a plain CUDA-core kernel used by tests to

@@ -31,6 +31,7 @@ class ConvDesc(C.Structure):
         ("head_weight", C.c_void_p), ("head_bias", C.c_void_p), ("head_n", C.c_int), ("head_out", C.c_void_p),
         ("in_layout", C.c_int),
         ("res_before_act", C.c_int),
+        ("out2", C.c_void_p), ("out2_C", C.c_int), ("out2_coff", C.c_int), ("out2_mode", C.c_int),
     ]
 
 
@@ -41,6 +42,7 @@ class YoloLevel(C.Structure):
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_SIGMOID = 0, 1, 2, 3
 OUT_F16_NHWC, OUT_F16_NHWC_UP2, OUT_F32_NHWC, OUT_F32_NCHW, OUT_NONE = 0, 1, 2, 3, 4
 IN_NHWC, IN_STEM4 = 0, 1
+OUT2_NONE, OUT2_UP2, OUT2_POOL2 = 0, 1, 2
 
 # name -> (restype, argtypes); must list every symbol of include/padel_b200.h (tests check this)
 _i, _p, _f = C.c_int, C.c_void_p, C.c_float

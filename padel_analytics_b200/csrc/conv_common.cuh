@@ -145,7 +145,7 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& kp, const Ep
 // while chunk i is activated, packed and stored -- and across the S sub-tiles of a halo tile.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool epilogue_fast_ok(const ConvKParams& kp) {
-  if ((kp.dbg_flags & 2) != 0) return false;
+  if ((kp.dbg_flags & 2) != 0 && kp.out2_mode == PB_OUT2_NONE) return false;
   if (kp.head_n != 0 || (kp.res != nullptr && ((kp.res_C | kp.res_coff) & 7) != 0)) return false;
   if ((reinterpret_cast<uintptr_t>(kp.out) & 31) != 0) return false;  // 32-byte stores
   if (kp.out_mode == PB_OUT_F16_NHWC || kp.out_mode == PB_OUT_F16_NHWC_UP2)
@@ -182,6 +182,9 @@ __device__ __forceinline__ void silu4(float& a, float& b, float& c, float& d) {
 struct EpiOut {
   int mode;       // PB_OUT_F16_NHWC | PB_OUT_F16_NHWC_UP2 | PB_OUT_F32_NHWC   (CTA-uniform)
   size_t dx, dy;  // UP2: bytes to the pixel one to the right / one row down in the upsampled tensor
+  int mode2;      // PB_OUT2_*: secondary output (CTA-uniform)
+  size_t dx2, dy2;  // PB_OUT2_UP2: the same strides in the secondary tensor
+  bool pool_writer;  // PB_OUT2_POOL2: this lane owns the top-left pixel of a 2x2 window
 };
 
 // bias + activation (+ residual) of one 16-column chunk of this thread's pixel
@@ -230,7 +233,7 @@ __device__ __forceinline__ void epi_compute16(int act, int has_res, bool plain_s
 
 __device__ __forceinline__ void epi_chunk(int act, int has_res, bool plain_silu, const EpiOut& eo, uint32_t (&r)[16],
                                           const float* __restrict__ sbias, char* op, const uint4 (&rv)[2], bool valid,
-                                          int nvalid) {
+                                          int nvalid, char* op2 = nullptr) {
   float v[16];
   epi_compute16(act, has_res, plain_silu, r, sbias, rv, v);
   if (eo.mode == PB_OUT_F32_NHWC) {
@@ -255,8 +258,31 @@ __device__ __forceinline__ void epi_chunk(int act, int has_res, bool plain_silu,
   __half2* h2 = reinterpret_cast<__half2*>(pk);
 #pragma unroll
   for (int j = 0; j < 8; ++j) h2[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+  if (eo.mode2 == PB_OUT2_POOL2) {
+    // 2x2 max over the lanes holding (row, col), (row, col^1), (row^1, col), (row^1, col^1) of the 4 x 8 pixel patch of
+    // this warp (lane = row_in_patch * 8 + col): two butterfly steps, executed by every lane (a window is entirely
+    // valid or entirely invalid: H, W and the tile origins are even)
+    uint4 mx[2] = {pk[0], pk[1]};
+    __half2* m2 = reinterpret_cast<__half2*>(mx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t w = *reinterpret_cast<uint32_t*>(&m2[j]);
+      uint32_t o = __shfl_xor_sync(0xffffffffu, w, 1);
+      m2[j] = __hmax2(m2[j], *reinterpret_cast<__half2*>(&o));
+      w = *reinterpret_cast<uint32_t*>(&m2[j]);
+      o = __shfl_xor_sync(0xffffffffu, w, 8);
+      m2[j] = __hmax2(m2[j], *reinterpret_cast<__half2*>(&o));
+    }
+    if (valid && eo.pool_writer) st_global_256(op2, mx[0], mx[1]);
+  }
   if (!valid) return;
   st_global_256(op, pk[0], pk[1]);
+  if (eo.mode2 == PB_OUT2_UP2) {
+    st_global_256(op2, pk[0], pk[1]);
+    st_global_256(op2 + eo.dx2, pk[0], pk[1]);
+    st_global_256(op2 + eo.dy2, pk[0], pk[1]);
+    st_global_256(op2 + eo.dy2 + eo.dx2, pk[0], pk[1]);
+  }
   if (eo.mode == PB_OUT_F16_NHWC_UP2) {
     st_global_256(op + eo.dx, pk[0], pk[1]);
     st_global_256(op + eo.dy, pk[0], pk[1]);
@@ -271,7 +297,7 @@ __device__ __forceinline__ void epi_chunk(int act, int has_res, bool plain_silu,
 __device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOut& eo, uint32_t t_addr0, int S,
                                               uint32_t sub_cols, int nch, int cout_n, const float* __restrict__ sbias,
                                               char* op0, const __half* rp0, size_t sub_out, size_t sub_res,
-                                              uint32_t valid_mask) {
+                                              uint32_t valid_mask, char* op20 = nullptr, size_t sub_out2 = 0) {
   uint32_t ra[16], rb[16];
   const int act = kp.act;
   const int has_res = kp.res != nullptr ? (kp.res_first ? 2 : 1) : 0;
@@ -297,7 +323,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOu
     tmem_ld_wait16(cur);                                                                                \
     if (more) tmem_ld16(t_addr0 + (uint32_t)jn * sub_cols + (uint32_t)(cn * 16), nxt);                  \
     epi_chunk(act, has_res, plain_silu, eo, cur, sbias + c * 16, op0 + (size_t)j * sub_out + (size_t)(c * cbytes), rv, valid, \
-              cout_n - c * 16);                                                                         \
+              cout_n - c * 16, op20 + (size_t)j * sub_out2 + (size_t)(c * 32));                          \
     if (!more) break;                                                                                   \
     j = jn;                                                                                             \
     c = cn;                                                                                             \

@@ -306,10 +306,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           eo.dy = (size_t)(2 * kp.Wo) * pxb;
           sub_out = 16 * pxb;
         }
+        eo.mode2 = kp.out2_mode;
+        eo.dx2 = eo.dy2 = 0;
+        eo.pool_writer = ((row | col) & 1) == 0;
+        char* obase2 = nullptr;
+        size_t sub_out2 = 0;
+        if (eo.mode2 != PB_OUT2_NONE) {
+          const size_t pxb2 = (size_t)kp.out2_C * 2;
+          size_t pix2;
+          if (eo.mode2 == PB_OUT2_UP2) {
+            pix2 = ((size_t)t.n * (2 * kp.Ho) + 2 * oh) * (2 * kp.Wo) + 2 * ow0;
+            eo.dx2 = pxb2;
+            eo.dy2 = (size_t)(2 * kp.Wo) * pxb2;
+            sub_out2 = 16 * pxb2;
+          } else {  // POOL2 (Ho, Wo even): the pooled pixel of the window whose top-left corner this lane holds
+            pix2 = ((size_t)t.n * (kp.Ho >> 1) + (oh >> 1)) * (kp.Wo >> 1) + (ow0 >> 1);
+            sub_out2 = 4 * pxb2;
+          }
+          obase2 = reinterpret_cast<char*>(kp.out2) + pix2 * pxb2 + (size_t)kp.out2_coff * 2;
+        }
         const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * kp.acc_cols);
         char* obase = reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)kp.out_coff * esz;
           epilogue_fast(kp, eo, t0, S, (uint32_t)kp.acc_cols, (kp.cout_store + 15) >> 4, kp.cout_store, tail->bias,
-                        obase, kp.res + pix0 * kp.res_C + kp.res_coff, sub_out, (size_t)8 * kp.res_C, vm);
+                        obase, kp.res + pix0 * kp.res_C + kp.res_coff, sub_out, (size_t)8 * kp.res_C, vm, obase2,
+                        sub_out2);
       } else
       for (int j = 0; j < S; ++j) {
         EpiPix px;

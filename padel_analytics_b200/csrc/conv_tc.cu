@@ -247,7 +247,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           char* obase = reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)(kp.out_coff + tc.nt * kp.BN) * esz;
           const __half* rbase = kp.res + px.pix * kp.res_C + kp.res_coff + tc.nt * kp.BN;
-            epilogue_fast(kp, eo, t_addr, 1, 0u, (cn + 15) >> 4, cn, sb, obase, rbase, 0, 0, px.valid ? 1u : 0u);
+          eo.mode2 = kp.out2_mode;  // PB_OUT2_NONE | PB_OUT2_UP2 here (pool windows do not map onto this tiling)
+          eo.dx2 = eo.dy2 = 0;
+          eo.pool_writer = false;
+          char* obase2 = nullptr;
+          if (eo.mode2 == PB_OUT2_UP2) {
+            const size_t pxb2 = (size_t)kp.out2_C * 2;
+            const size_t pix2 = ((size_t)px.n * (2 * kp.Ho) + 2 * px.oh) * (2 * kp.Wo) + 2 * px.ow;
+            eo.dx2 = pxb2;
+            eo.dy2 = (size_t)(2 * kp.Wo) * pxb2;
+            obase2 = reinterpret_cast<char*>(kp.out2) + pix2 * pxb2 + (size_t)(kp.out2_coff + tc.nt * kp.BN) * 2;
+          }
+            epilogue_fast(kp, eo, t_addr, 1, 0u, (cn + 15) >> 4, cn, sb, obase, rbase, 0, 0, px.valid ? 1u : 0u, obase2,
+                          0);
         }
       } else
       for (int c = 0; c < kp.BN; c += 32) {
@@ -363,6 +375,19 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     PB_CHECK(d->res_C % 8 == 0 && d->res_coff % 8 == 0 && (reinterpret_cast<uintptr_t>(d->res) & 15) == 0,
              "conv: residual must be 16-byte aligned slices");
   }
+  PB_CHECK(d->out2_mode >= PB_OUT2_NONE && d->out2_mode <= PB_OUT2_POOL2, "conv: bad out2_mode");
+  if (d->out2_mode != PB_OUT2_NONE) {
+    // the secondary store lives in the vectorised epilogue only: 32-byte channel groups on both outputs
+    PB_CHECK(d->out_mode == PB_OUT_F16_NHWC && d->head_n == 0 && !stem, "conv: out2 needs a plain f16 NHWC primary output");
+    PB_CHECK(d->out2 && (reinterpret_cast<uintptr_t>(d->out2) & 31) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 31) == 0,
+             "conv: out2 pointers must be 32-byte aligned");
+    PB_CHECK(d->cout_store % 16 == 0 && d->out_C % 16 == 0 && d->out_coff % 16 == 0 && d->out2_C % 16 == 0 &&
+                 d->out2_coff % 16 == 0 && d->out2_coff >= 0 && d->out2_coff + d->cout_store <= d->out2_C,
+             "conv: out2 needs 16-channel aligned slices");
+    if (d->out2_mode == PB_OUT2_POOL2)
+      PB_CHECK(d->ksize == 3 && d->stride == 1 && d->H % 2 == 0 && d->W % 2 == 0,
+               "conv: PB_OUT2_POOL2 needs a 3x3 stride-1 conv on even H, W");
+  }
   EncodeTiledFn encode = get_encode_fn();
   PB_CHECK(encode != nullptr, "conv: cuTensorMapEncodeTiled not available (no CUDA driver?)");
 
@@ -389,6 +414,10 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
   kp.out_coff = d->out_coff;
   kp.out_mode = d->out_mode;
   kp.cout_store = d->cout_store;
+  kp.out2 = d->out2;
+  kp.out2_C = d->out2_C;
+  kp.out2_coff = d->out2_coff;
+  kp.out2_mode = d->out2_mode;
   kp.head_w = d->head_weight;
   kp.head_b = d->head_bias;
   kp.head_n = d->head_n;
@@ -410,6 +439,7 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
       if (rc >= 0) return rc;
     }
   }
+  PB_CHECK(d->out2_mode != PB_OUT2_POOL2, "conv: PB_OUT2_POOL2 is only implemented by the halo kernel (cout <= 192)");
   // N tile: largest multiple-of-16 divisor of cout_pad that is <= 256
   int nn = (d->cout_pad + 255) / 256;
   while (d->cout_pad % nn != 0 || (d->cout_pad / nn) % 16 != 0) ++nn;

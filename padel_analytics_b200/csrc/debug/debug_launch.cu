@@ -118,7 +118,10 @@ extern "C" int pb_debug_launch_chain(long long* out, int variant, int n, void* s
     PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(dbg_launch_pieces), 120 * 1024));
     static void* gstore = nullptr;
     if (gstore == nullptr) PB_CUDA(cudaMalloc(&gstore, (size_t)148 * 480 * 128));
-    for (int i = 0; i < n; ++i) dbg_launch_pieces<<<148, 480, 120 * 1024, s>>>(tm, out, i, variant, gstore);
+    // variants 11 / 12: variant 10 on 37 / 74 CTAs (is the TMA pull bound per SM or by aggregate L2 bandwidth?)
+    const int grid = variant == 11 ? 37 : (variant == 12 ? 74 : 148);
+    const int level = variant > 10 ? 10 : variant;
+    for (int i = 0; i < n; ++i) dbg_launch_pieces<<<grid, 480, 120 * 1024, s>>>(tm, out, i, level, gstore);
     PB_CUDA(cudaGetLastError());
     return 0;
   }

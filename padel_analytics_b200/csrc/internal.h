@@ -137,6 +137,8 @@ struct ConvKParams {
   int res_first;  // 1: residual added before the activation (ResNet), 0: after (YOLO Bottleneck)
   void* out;
   int out_C, out_coff, out_mode, cout_store;
+  void* out2;  // secondary output (PB_OUT2_*), fast epilogue only
+  int out2_C, out2_coff, out2_mode;
   uint32_t idesc;
   uint32_t a_bytes, b_bytes, b_tx_bytes;
   int acc_stages, acc_cols;  // TMEM accumulator ring: acc_stages buffers, acc_cols columns apart

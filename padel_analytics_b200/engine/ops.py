@@ -43,9 +43,11 @@ def pack_conv_weight(w: torch.Tensor, b: torch.Tensor | None, cin_pad: int, cout
 def make_conv_desc(x: torch.Tensor, c_in_off: int, cin: int, w: torch.Tensor, b: torch.Tensor, ksize: int,
                    stride: int, act: int, out: torch.Tensor, out_coff: int, out_mode: int = L.OUT_F16_NHWC,
                    cout_store: int | None = None, res: torch.Tensor | None = None, res_coff: int = 0,
-                   head: tuple | None = None, res_before_act: bool = False) -> L.ConvDesc:
+                   head: tuple | None = None, res_before_act: bool = False,
+                   out2: tuple | None = None) -> L.ConvDesc:
     """x: NHWC half tensor (N,H,W,C). w: packed half [taps][cout_pad][cin]. out: NHWC tensor (half or float), or
-    (N,C,H,W) float for OUT_F32_NCHW."""
+    (N,C,H,W) float for OUT_F32_NCHW. out2 = (NHWC half tensor, first channel, L.OUT2_UP2 | L.OUT2_POOL2): the same
+    values written a second time, 2x2-replicated or 2x2-max-pooled (no separate upsample / pool launch)."""
     N, H, W, Ct = x.shape
     cout_pad = w.shape[1]
     assert w.shape[2] == cin and w.shape[0] == ksize * ksize
@@ -73,6 +75,12 @@ def make_conv_desc(x: torch.Tensor, c_in_off: int, cin: int, w: torch.Tensor, b:
     d.out_C = out.shape[-1] if out_mode != L.OUT_F32_NCHW else out.shape[1]
     d.out_coff, d.out_mode = out_coff, out_mode
     d.cout_store = cout_pad if cout_store is None else cout_store
+    if out2 is not None:
+        t2, off2, mode2 = out2
+        Ho, Wo = H // stride, W // stride
+        want = (N, 2 * Ho, 2 * Wo) if mode2 == L.OUT2_UP2 else (N, Ho // 2, Wo // 2)
+        assert tuple(t2.shape[:3]) == want and t2.dtype == torch.float16, (t2.shape, want)
+        d.out2, d.out2_C, d.out2_coff, d.out2_mode = t2.data_ptr(), t2.shape[-1], off2, mode2
     return d
 
 

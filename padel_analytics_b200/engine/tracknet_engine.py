@@ -99,17 +99,24 @@ class TrackNetEngine:
         W_ = self._w
         R, UP, SIG = L.ACT_RELU, L.OUT_F16_NHWC_UP2, L.ACT_SIGMOID
 
-        def conv(x, coff, cin, name, out, ooff, mode=L.OUT_F16_NHWC, act=R, k=3, store=None):
+        def conv(x, coff, cin, name, out, ooff, mode=L.OUT_F16_NHWC, act=R, k=3, store=None, pool=None):
             w, b = W_[name]
-            P.conv(ops.make_conv_desc(x, coff, cin, w, b, k, 1, act, out, ooff, mode, store),
+            P.conv(ops.make_conv_desc(x, coff, cin, w, b, k, 1, act, out, ooff, mode, store,
+                                      out2=None if pool is None else (pool, 0, L.OUT2_POOL2)),
                    cin_real=27 if name == "down_block_1.conv_1" else cin)
 
+        # MaxPool2d of the first two encoder blocks (models.py:60,62) is a second store of the producing conv
+        # (PB_OUT2_POOL2); PADEL_B200_FUSE_OUT2=0 keeps the separate pool launches (A/B)
+        fuse = os.environ.get("PADEL_B200_FUSE_OUT2", "1") != "0"
+
         conv(self.x, 0, 32, "down_block_1.conv_1", self.t1, 0)
-        conv(self.t1, 0, 64, "down_block_1.conv_2", self.cat3, 128)
-        P.maxpool2(self.cat3, 128, 64, self.p1, 0)
+        conv(self.t1, 0, 64, "down_block_1.conv_2", self.cat3, 128, pool=self.p1 if fuse else None)
+        if not fuse:
+            P.maxpool2(self.cat3, 128, 64, self.p1, 0)
         conv(self.p1, 0, 64, "down_block_2.conv_1", self.t2, 0)
-        conv(self.t2, 0, 128, "down_block_2.conv_2", self.cat2, 256)
-        P.maxpool2(self.cat2, 256, 128, self.p2, 0)
+        conv(self.t2, 0, 128, "down_block_2.conv_2", self.cat2, 256, pool=self.p2 if fuse else None)
+        if not fuse:
+            P.maxpool2(self.cat2, 256, 128, self.p2, 0)
         conv(self.p2, 0, 128, "down_block_3.conv_1", self.t3a, 0)
         conv(self.t3a, 0, 256, "down_block_3.conv_2", self.t3b, 0)
         conv(self.t3b, 0, 256, "down_block_3.conv_3", self.cat1, 512)

@@ -10,6 +10,7 @@ reads and writes (no copies except the two nearest-upsamples and SPPF pooling).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -137,14 +138,15 @@ class YoloEngine:
 
         SILU = L.ACT_SILU
 
-        def conv(x, coff, cin, prefix, out, ooff, k, s, res=None, res_off=0):
+        def conv(x, coff, cin, prefix, out, ooff, k, s, res=None, res_off=0, up=None):
             cout = self._cout(prefix)
             w, b = self._wb(prefix, cin, ops.pad16(cout))
-            P.conv(ops.make_conv_desc(x, coff, cin, w, b, k, s, SILU, out, ooff, L.OUT_F16_NHWC, None, res, res_off),
+            P.conv(ops.make_conv_desc(x, coff, cin, w, b, k, s, SILU, out, ooff, L.OUT_F16_NHWC, None, res, res_off,
+                                      out2=None if up is None else (up, 0, L.OUT2_UP2)),
                    cin_real=self.sd[f"{prefix}.conv.weight"].shape[1], cout_real=cout)
             return ops.pad16(cout)
 
-        def c2f(x, coff, cin, i, out, ooff, shortcut):
+        def c2f(x, coff, cin, i, out, ooff, shortcut, up=None):
             """ultralytics C2f (App. A.2): cv1 -> [y0,y1] ; y_{j+2} = Bottleneck_j(y_{j+1}) ; cv2(cat(y))."""
             pre = f"model.{i}"
             c = self._cout(f"{pre}.cv1") // 2
@@ -160,8 +162,11 @@ class YoloEngine:
                 conv(cat, (1 + j) * c, c, f"{pre}.m.{j}.cv1", tmp, 0, 3, 1)
                 conv(tmp, 0, c, f"{pre}.m.{j}.cv2", cat, (2 + j) * c, 3, 1, res=cat if shortcut else None,
                      res_off=(1 + j) * c)
-            conv(cat, 0, ccat, f"{pre}.cv2", out, ooff, 1, 1)
+            conv(cat, 0, ccat, f"{pre}.cv2", out, ooff, 1, 1, up=up)
 
+        # the two nn.Upsample(2, "nearest") of the neck (layers 10, 13) are a second, replicated store of the
+        # producing 1x1 conv (PB_OUT2_UP2); PADEL_B200_FUSE_OUT2=0 keeps the separate upsample launches (A/B)
+        fuse = os.environ.get("PADEL_B200_FUSE_OUT2", "1") != "0"
         c0, c1, c2, c3, c4 = (self._cout(f"model.{i}") for i in (0, 1, 3, 5, 7))
         for c in (c0, c1, c2, c3, c4):
             if c % 16:
@@ -197,10 +202,12 @@ class YoloEngine:
         c2f(b7, 0, c4, 8, b8, 0, True)
         conv(b8, 0, c4, "model.9.cv1", sp, 0, 1, 1)  # SPPF
         P.sppf_pool(sp, c4 // 2)
-        conv(sp, 0, 4 * (c4 // 2), "model.9.cv2", cat20, c3, 1, 1)  # P5
-        P.upsample2(cat20, c3, c4, cat11, 0)  # layers 10-11
-        c2f(cat11, 0, c4 + c3, 12, cat17, c2, False)  # h4
-        P.upsample2(cat17, c2, c3, cat14, 0)  # layers 13-14
+        conv(sp, 0, 4 * (c4 // 2), "model.9.cv2", cat20, c3, 1, 1, up=cat11 if fuse else None)  # P5 (+ layers 10-11)
+        if not fuse:
+            P.upsample2(cat20, c3, c4, cat11, 0)  # layers 10-11
+        c2f(cat11, 0, c4 + c3, 12, cat17, c2, False, up=cat14 if fuse else None)  # h4 (+ layers 13-14)
+        if not fuse:
+            P.upsample2(cat17, c2, c3, cat14, 0)  # layers 13-14
         c2f(cat14, 0, c3 + c2, 15, o3, 0, False)
         conv(o3, 0, c2, "model.16", cat17, 0, 3, 2)
         c2f(cat17, 0, c2 + c3, 18, o4, 0, False)

@@ -12,7 +12,7 @@ fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
 names = ["148x480, no smem, int param", "+ 120 KB dynamic smem", "+ 640-byte struct param",
          "+ two CUtensorMap __grid_constant__ params", "same, programmatic stream serialization",
          "120 KB smem + tcgen05.alloc/dealloc 512 columns", "+ mbarrier init", "+ one 4 KB TMA load", "+ one UMMA + commit",
-         "+ 32-byte global store per thread", "+ 32 more TMA boxes in flight at exit (waited)"]
+         "+ 32-byte global store per thread", "+ 32 more TMA boxes in flight at exit (waited)", "variant 10 on 37 CTAs", "variant 10 on 74 CTAs"]
 n = 40
 for v, name in enumerate(names):
     out = torch.zeros(n, dtype=torch.int64, device="cuda")

@@ -208,3 +208,50 @@ def test_halo_conv_cta_pair_mode(case, monkeypatch):
     monkeypatch.setenv("PADEL_B200_CONV_PAIR", "1")
     bad, mx = run_case(**case)
     assert bad == 0.0, f"pair-mode kernel: {bad*100:.3f}% elements out of tolerance (max err {mx})"
+
+
+OUT2_CASES = [
+    # YOLO neck: 1x1 conv whose output also feeds nn.Upsample(2) -> concat slice (layers 9->10->11, 12->13->14)
+    dict(N=2, H=12, W=20, cin=512, cout=256, k=1, mode=L.OUT2_UP2, act=L.ACT_SILU),
+    dict(N=3, H=24, W=40, cin=192, cout=128, k=1, mode=L.OUT2_UP2, act=L.ACT_SILU),
+    dict(N=1, H=20, W=20, cin=960, cout=576, k=1, mode=L.OUT2_UP2, act=L.ACT_SILU),  # m scale: 3 N tiles of 192
+    dict(N=2, H=16, W=32, cin=64, cout=64, k=3, mode=L.OUT2_UP2, act=L.ACT_RELU),
+    # TrackNet encoder: 3x3 conv + MaxPool2d(2) (models.py:58-62); single-CTA and CTA-pair tiles, ragged edges
+    dict(N=2, H=288, W=512, cin=64, cout=64, k=3, mode=L.OUT2_POOL2, act=L.ACT_RELU),
+    dict(N=3, H=144, W=256, cin=128, cout=128, k=3, mode=L.OUT2_POOL2, act=L.ACT_RELU),
+    dict(N=2, H=36, W=44, cin=32, cout=48, k=3, mode=L.OUT2_POOL2, act=L.ACT_RELU),
+    dict(N=1, H=18, W=10, cin=16, cout=16, k=3, mode=L.OUT2_POOL2, act=L.ACT_SILU),
+]
+
+
+@pytest.mark.parametrize("case", OUT2_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_secondary_output_is_the_upsampled_or_pooled_primary(case):
+    """PB_OUT2_UP2 / PB_OUT2_POOL2: the second tensor must be EXACTLY nearest-upsample / 2x2 max-pool of the fp16 primary
+    output (same rounded values, so bit-exact), inside its channel slice only; the primary equals the plain conv."""
+    N, H, W, cin, cout, k, mode, act = (case[q] for q in ("N", "H", "W", "cin", "cout", "k", "mode", "act"))
+    g = torch.Generator().manual_seed(5)
+    dev = "cuda"
+    x = torch.randn(N, H, W, cin, generator=g).half().to(dev)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    wp, bp = ops.pack_conv_weight(w, b, cin, cout, dev)
+    off1, off2 = 16, 32
+    out = torch.full((N, H, W, cout + off1 + 16), 7.0, dtype=torch.float16, device=dev)
+    plain = torch.zeros((N, H, W, cout), dtype=torch.float16, device=dev)
+    shape2 = (N, 2 * H, 2 * W) if mode == L.OUT2_UP2 else (N, H // 2, W // 2)
+    out2 = torch.full((*shape2, cout + off2 + 16), 5.0, dtype=torch.float16, device=dev)
+    ops.conv2d(ops.make_conv_desc(x, 0, cin, wp, bp, k, 1, act, plain, 0))
+    ops.conv2d(ops.make_conv_desc(x, 0, cin, wp, bp, k, 1, act, out, off1, out2=(out2, off2, mode)))
+    torch.cuda.synchronize()
+    prim = out[..., off1:off1 + cout]
+    assert torch.equal(prim, plain)
+    assert torch.all(out[..., :off1] == 7.0) and torch.all(out[..., off1 + cout:] == 7.0)
+    p = prim.permute(0, 3, 1, 2).float()
+    want = F.interpolate(p, scale_factor=2, mode="nearest") if mode == L.OUT2_UP2 else F.max_pool2d(p, 2, 2)
+    got = out2[..., off2:off2 + cout].permute(0, 3, 1, 2).float()
+    assert torch.equal(got, want)
+    assert torch.all(out2[..., :off2] == 5.0) and torch.all(out2[..., off2 + cout:] == 5.0)
+    # and the plain conv is the usual one
+    y = ACT[act](F.conv2d(x.cpu().float().permute(0, 3, 1, 2), w.half().float(), b, padding=k // 2))
+    err = (plain.cpu().float().permute(0, 3, 1, 2) - y).abs()
+    assert ((err > 2e-3 + 2e-3 * y.abs()).float().mean().item()) == 0
