@@ -204,6 +204,9 @@ void pb_bytetrack_reset(pb_bytetrack* bt);
 /* One frame: boxes float (n,4) xyxy, scores float (n) (HOST pointers) -> ids_out int (n): the track id attached to each
  * detection, -1 for detections without an active track (dropped by update_with_detections).                      */
 int pb_bytetrack_update(pb_bytetrack* bt, const float* boxes, const float* scores, int n, int* ids_out);
+/* the same for `frames` consecutive frames: counts int (frames), boxes / scores / ids_out concatenated in frame order */
+int pb_bytetrack_update_many(pb_bytetrack* bt, const float* boxes, const float* scores, const int* counts, int frames,
+                             int* ids_out);
 
 /* ---- InpaintNet (ball_tracker/models.py:101-130, called at ball_tracker.py:573-576) ----------------------- */
 /* coor float (N,L,2) normalised coordinates, mask float (N,L) inpaint mask -> out float (N,L,2) = sigmoid(net).

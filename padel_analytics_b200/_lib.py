@@ -79,6 +79,7 @@ SIGNATURES = {
     "pb_bytetrack_destroy": (None, [_p]),
     "pb_bytetrack_reset": (None, [_p]),
     "pb_bytetrack_update": (_i, [_p, _p, _p, _i, _p]),
+    "pb_bytetrack_update_many": (_i, [_p, _p, _p, _p, _i, _p]),
     "pb_inpaintnet_forward": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "pb_median_u8": (_i, [_p, _i, C.c_longlong, _p, _i, _p]),
     "pb_tracknet_ensemble": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p]),

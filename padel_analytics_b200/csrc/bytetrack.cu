@@ -389,4 +389,20 @@ int pb_bytetrack_update(pb_bytetrack* bt, const float* boxes, const float* score
   return 0;
 }
 
+/* `frames` consecutive frames in one call: counts int (frames) detections per frame, boxes / scores / ids_out the
+ * frames' detections back to back.  Identical to calling pb_bytetrack_update once per frame. */
+int pb_bytetrack_update_many(pb_bytetrack* bt, const float* boxes, const float* scores, const int* counts, int frames,
+                             int* ids_out) {
+  PB_CHECK(bt != nullptr && frames >= 0 && (frames == 0 || counts), "bytetrack_update_many: null argument");
+  size_t at = 0;
+  for (int f = 0; f < frames; ++f) {
+    const int n = counts[f];
+    PB_CHECK(n >= 0, "bytetrack_update_many: negative count at frame %d", f);
+    const int rc = pb_bytetrack_update(bt, boxes + 4 * at, scores + at, n, ids_out + at);
+    if (rc != 0) return rc;
+    at += (size_t)n;
+  }
+  return 0;
+}
+
 }  // extern "C"

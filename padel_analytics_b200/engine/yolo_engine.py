@@ -66,6 +66,70 @@ class Result:
     orig_shape: tuple
 
 
+class ResultBlock:
+    """The Results of consecutive frames as ONE dense array: rows (n, cap, 6 + K*D) float32 = [x1, y1, x2, y2, conf,
+    cls, keypoints...] per detection (score-sorted, rows at and beyond counts[i] are padding) + counts (n,) int32.
+    A read-only sequence of `Result`s (built on demand, views into the block) for code written against ultralytics'
+    list of Results; the trackers' post-processing and the multi-GPU gather read the arrays directly -- at thousands
+    of frames per second a Python object per frame and tracker is the expensive part of the host side."""
+
+    __slots__ = ("rows", "counts", "kpt_shape", "names", "orig_shape", "_t")
+
+    def __init__(self, rows: np.ndarray, counts: np.ndarray, kpt_shape, names, orig_shape):
+        self.rows, self.counts, self.kpt_shape, self.names, self.orig_shape = rows, counts, kpt_shape, names, orig_shape
+        self._t = None
+
+    def __len__(self):
+        return self.rows.shape[0]
+
+    @property
+    def keypoints(self) -> np.ndarray | None:
+        """(n, cap, K, D) view of the keypoint columns"""
+        if not self.kpt_shape:
+            return None
+        n, cap = self.rows.shape[:2]
+        return self.rows[..., 6:].reshape(n, cap, *self.kpt_shape)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            a, b, step = i.indices(len(self))
+            if step != 1:
+                raise IndexError("ResultBlock: contiguous slices only")
+            return ResultBlock(self.rows[a:b], self.counts[a:b], self.kpt_shape, self.names, self.orig_shape)
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        if self._t is None:
+            kp = self.keypoints
+            self._t = (torch.from_numpy(self.rows[..., :6]), torch.from_numpy(kp) if kp is not None else None)
+        c = int(self.counts[i])
+        bt, kt = self._t
+        return Result(Boxes(bt[i, :c]), Keypoints(kt[i, :c]) if kt is not None else None, self.names, self.orig_shape)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    @staticmethod
+    def concat(blocks: list, like: "ResultBlock | None" = None) -> "ResultBlock":
+        """Frames of several blocks in order, padded to the largest per-frame count (padding rows zeroed)."""
+        ref = blocks[0] if blocks else like
+        rowlen = ref.rows.shape[2]
+        cap = max([int(b.counts.max()) for b in blocks if len(b)], default=0)
+        cap = max(cap, 1)
+        n = sum(len(b) for b in blocks)
+        rows = np.zeros((n, cap, rowlen), dtype=np.float32)
+        counts = np.zeros((n,), dtype=np.int32)
+        at = 0
+        for b in blocks:
+            m, c = len(b), min(cap, b.rows.shape[1])
+            rows[at:at + m, :c] = b.rows[:, :c]
+            counts[at:at + m] = b.counts
+            at += m
+        rows[np.arange(cap)[None, :] >= counts[:, None]] = 0
+        return ResultBlock(rows, counts, ref.kpt_shape, ref.names, ref.orig_shape)
+
+
 def _kpad(c: int) -> int:
     """Channel count a conv should READ: widths in (32, 64) or not a multiple of 64 above that are rounded up to a
     multiple of 64 (zero channels in the buffer, zero weights), so the kernel runs 64-channel K blocks (128-byte rows,
@@ -406,17 +470,19 @@ class YoloEngine:
     def _detect_finish(self, handle):
         return self._detect_resolve(handle)
 
-    def _results(self, rows, counts, n, net_hw, orig_hw):
+    def _results_block(self, rows, counts, n, net_hw, orig_hw) -> ResultBlock:
         """scale_boxes / scale_coords / clip / keypoint conf<0.5 -> 0 (ultralytics ops, SURVEY App. A.4 vi-vii),
-        float32 arithmetic on the host, one vectorised pass over the whole (n, max_det, 6+nk) block (the padding rows
-        beyond each image's count are transformed too and never looked at)."""
+        float32 arithmetic on the host, one vectorised pass over the whole (n, cap, 6+nk) block, cap = the largest
+        per-image count (the padding rows beyond each image's own count are transformed too and never looked at)."""
         h1, w1 = net_hw
         h0, w0 = orig_hw
         gain = min(h1 / h0, w1 / w0)
         padb = (round((w1 - w0 * gain) / 2 - 0.1), round((h1 - h0 * gain) / 2 - 0.1))
         padk = ((w1 - w0 * gain) / 2, (h1 - h0 * gain) / 2)
         g32 = np.float32(gain)
-        r = rows[:n].astype(np.float32, copy=True)
+        counts = np.asarray(counts[:n], dtype=np.int32)
+        cap = max(int(counts.max()) if n else 0, 1)  # only the rows some image uses are transformed and kept
+        r = rows[:n, :cap].astype(np.float32, copy=True)
         box = r[..., :6]
         box[..., [0, 2]] -= np.float32(padb[0])
         box[..., [1, 3]] -= np.float32(padb[1])
@@ -439,14 +505,10 @@ class YoloEngine:
                 m = kall[..., 2] < 0.5
                 kall[..., 0][m] = 0
                 kall[..., 1][m] = 0
-        boxes_t = torch.from_numpy(np.ascontiguousarray(box))
-        kp_t = torch.from_numpy(np.ascontiguousarray(kall)) if kall is not None else None
-        res = []
-        for i in range(n):
-            c = int(counts[i])
-            res.append(Result(Boxes(boxes_t[i, :c]), Keypoints(kp_t[i, :c]) if kp_t is not None else None, self.names,
-                              (h0, w0)))
-        return res
+        return ResultBlock(r, counts, self.kpt_shape, self.names, (h0, w0))
+
+    def _results(self, rows, counts, n, net_hw, orig_hw) -> list:
+        return list(self._results_block(rows, counts, n, net_hw, orig_hw))
 
     @torch.no_grad()
     def predict(self, source, conf=0.25, iou=0.7, imgsz=640, device=None, classes=None, max_det=300, **kw):
@@ -485,7 +547,7 @@ class YoloEngine:
         else:
             raise L.PbError(f"unknown prep {prep!r}")
         rows, counts = self._detect(st, n, conf, iou, classes, max_det)
-        return self._results(rows, counts, n, (st["Hn"], st["Wn"]), orig)
+        return self._results_block(rows, counts, n, (st["Hn"], st["Wn"]), orig)
 
     @torch.no_grad()
     def predict_frames_async(self, frames, prep: str, conf, iou, imgsz, classes=None, max_det=300):
@@ -504,6 +566,6 @@ class YoloEngine:
 
         def finish():
             rows, counts = self._detect_finish(handle)
-            return self._results(rows, counts, n, (st["Hn"], st["Wn"]), orig)
+            return self._results_block(rows, counts, n, (st["Hn"], st["Wn"]), orig)
 
         return finish

@@ -9,7 +9,7 @@ from typing import Iterable, Optional, Type
 
 import numpy as np
 
-from ..engine.yolo_engine import YoloEngine
+from ..engine.yolo_engine import ResultBlock, YoloEngine
 from .tracker import NoPredictFrames, NoPredictSample, Object, Tracker
 
 
@@ -127,6 +127,12 @@ class KeypointsTracker(Tracker):
         ratio_x = frame_hw[1] / self.TRAIN_IMAGE_SIZE
         ratio_y = frame_hw[0] / self.TRAIN_IMAGE_SIZE
         out = []
+        if isinstance(results, ResultBlock):  # the same arithmetic over the whole block of frames at once
+            top = (results.keypoints[:, 0, :, :2].astype(np.float64) * np.array([ratio_x, ratio_y])).tolist()
+            for c, xy in zip(results.counts.tolist(), top):
+                out.append(Keypoints([Keypoint(id=self.POINTS_MAPPER[i], xy=(x, y)) for i, (x, y) in enumerate(xy)]
+                                     if c else []))
+            return out
         for result in results:
             kps = []
             if len(result.keypoints.xy):

@@ -7,7 +7,7 @@ from typing import Iterable, Optional, Type
 
 import numpy as np
 
-from ..engine.yolo_engine import YoloEngine
+from ..engine.yolo_engine import ResultBlock, YoloEngine
 from .tracker import NoPredictFrames, Object, Tracker
 
 
@@ -185,6 +185,9 @@ class PlayerKeypointsTracker(Tracker):
         ratio_y = frame_hw[0] / self.train_image_size
         out = []
         names = PlayerKeypoints.KEYPOINTS_NAMES
+        if isinstance(results, ResultBlock):  # the same arithmetic over the whole block of frames at once
+            xy = results.keypoints[..., :2].astype(np.float64) * np.array([ratio_x, ratio_y])
+            return [PlayersKeypoints.from_xy(xy[i, :c]) for i, c in enumerate(results.counts.tolist())]
         for result in results:
             # float32 -> Python float (exact) * Python float ratio, as `keypoint[0].item() * ratio_x` does (:306-309)
             xy = result.keypoints.xy.numpy().astype(np.float64) * np.array([ratio_x, ratio_y])

@@ -7,7 +7,7 @@ from typing import Iterable, Optional, Type
 
 import numpy as np
 
-from ..engine.yolo_engine import YoloEngine
+from ..engine.yolo_engine import ResultBlock, YoloEngine
 from . import sv_compat as sv
 from .tracker import NoPredictFrames, Object, Tracker
 
@@ -183,6 +183,8 @@ class PlayerTracker(Tracker):
 
     def postprocess(self, results) -> list[Players]:
         """Polygon filter + ByteTrack ids (players_tracker.py:362-378); sequential, frame order matters."""
+        if isinstance(results, ResultBlock) and hasattr(self.byte_track, "update_many"):
+            return self._postprocess_block(results)
         out = []
         for result in results:
             det = sv.Detections.from_ultralytics(result)
@@ -190,6 +192,31 @@ class PlayerTracker(Tracker):
                 det = det[self.polygon_zone.trigger(det)]
             det = self.byte_track.update_with_detections(detections=det)
             out.append(Players.from_rows(det.xyxy, det.tracker_id, det.class_id, det.confidence))
+        return out
+
+    def _postprocess_block(self, block: ResultBlock) -> list[Players]:
+        """The same stage over a dense block of frames: one polygon test over all detections, one native ByteTrack call
+        for all frames (`pb_bytetrack_update_many`), result objects as views into the surviving rows."""
+        n, cap = block.rows.shape[:2]
+        counts = block.counts.astype(np.int64)
+        valid = np.arange(cap)[None, :] < counts[:, None]  # (n, cap) row-major = frame order, score order within
+        det = block.rows[valid]  # (total, rowlen)
+        frame_of = np.repeat(np.arange(n), counts)
+        if self.polygon_zone is not None and len(det):
+            keep = self.polygon_zone.trigger(sv.Detections(xyxy=det[:, :4]))
+            det, frame_of = det[keep], frame_of[keep]
+        xyxy = np.ascontiguousarray(det[:, :4])
+        conf = np.ascontiguousarray(det[:, 4])
+        per_frame = np.bincount(frame_of, minlength=n).astype(np.int32)
+        ids = self.byte_track.update_many(xyxy, conf, per_frame)
+        tracked = ids != -1
+        xyxy, conf, ids = xyxy[tracked], conf[tracked], ids[tracked].astype(int)
+        cid = det[tracked, 5].astype(int)
+        ends = np.cumsum(np.bincount(frame_of[tracked], minlength=n)).tolist()
+        out, a = [], 0
+        for b in ends:
+            out.append(Players.from_rows(xyxy[a:b], ids[a:b], cid[a:b], conf[a:b]))
+            a = b
         return out
 
     def predict_sample(self, sample: Iterable[np.ndarray], **kwargs) -> list[Players]:

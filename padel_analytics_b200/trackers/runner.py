@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import sv_compat as sv
+from ..engine.yolo_engine import ResultBlock
 from .ball_tracker import Ball, BallTracker
 from .keypoints_tracker import KeypointsTracker
 from .players_keypoints_tracker import PlayerKeypointsTracker
@@ -337,8 +338,12 @@ class TrackingRunner:
                     else:
                         res = out[name]
                         n = len(res)
-                        keep = [r for k, r in enumerate(res) if lo <= pos + k < hi]
-                        parts[name] += keep
+                        a, b = max(lo - pos, 0), min(hi - pos, n)  # halo frames of a ball shard are dropped
+                        if b > a:
+                            if isinstance(res, ResultBlock):
+                                parts[name].append(res[a:b])
+                            else:
+                                parts[name] += res[a:b]
                 pos += n if n is not None else B
         torch.cuda.synchronize()
         t_pass = timeit.default_timer() - t0
@@ -349,8 +354,8 @@ class TrackingRunner:
                 for d in parts[name]:
                     xyv.update(d)
                 part = _ball_records(xyv, lo, hi)
-            elif not dist_on:
-                part = parts[name]  # already post-processed objects, in frame order
+            elif not dist_on or not all(isinstance(p, ResultBlock) for p in parts[name]):
+                part = parts[name]  # already post-processed (or fixed) objects, in frame order
             else:
                 part = (_yolo_records(parts[name], t), hw)
             self._gather_and_assemble(t, part, total, rank, world, dist_on)
@@ -390,10 +395,13 @@ class TrackingRunner:
                 Ball(frame=n, xy=(xyv[n][0], xyv[n][1]), visibility=xyv[n][2]) if n in xyv
                 else Ball(frame=n, xy=(0.0, 0.0), visibility=0) for n in range(total)]
         elif parts and isinstance(parts[0], tuple):
-            results, hw = [], None
-            for res, h in parts:
-                results += res.to_results(tracker) if isinstance(res, YoloRecords) else res
-                hw = hw or h
+            hw = next((h for _, h in parts if h), None)
+            if all(isinstance(res, YoloRecords) for res, _ in parts):  # dense records: stay dense
+                results = ResultBlock.concat([res.to_results(tracker) for res, _ in parts])
+            else:
+                results = []
+                for res, _ in parts:
+                    results += list(res.to_results(tracker)) if isinstance(res, YoloRecords) else list(res)
             if isinstance(tracker, PlayerTracker):
                 tracker.results.predictions = tracker.postprocess(results)  # ordered => ByteTrack ids are consistent
             else:
@@ -405,24 +413,13 @@ class TrackingRunner:
 # ---- fixed-capacity records for the gather ---------------------------------------------------------
 class YoloRecords:
     """Detections of consecutive frames as one dense float32 block (frames, cap, 6 + K*D) + int32 counts: rows are
-    [x1, y1, x2, y2, conf, cls, keypoints...] exactly as the engine's Results hold them."""
+    [x1, y1, x2, y2, conf, cls, keypoints...] exactly as the engine's ResultBlock holds them."""
 
     def __init__(self, rows: torch.Tensor, counts: torch.Tensor, kpt_shape):
         self.rows, self.counts, self.kpt_shape = rows, counts, kpt_shape
 
-    def to_results(self, tracker) -> list:
-        from ..engine.yolo_engine import Boxes, Keypoints, Result
-
-        out = []
-        names = tracker.model.names
-        for i in range(self.rows.shape[0]):
-            r = self.rows[i, : int(self.counts[i])]
-            kp = None
-            if self.kpt_shape:
-                K, D = self.kpt_shape
-                kp = Keypoints(r[:, 6:].reshape(-1, K, D).clone())
-            out.append(Result(Boxes(r[:, :6].clone()), kp, names, None))
-        return out
+    def to_results(self, tracker) -> ResultBlock:
+        return ResultBlock(self.rows.numpy(), self.counts.numpy(), self.kpt_shape, tracker.model.names, None)
 
 
 class BallRecords:
@@ -435,28 +432,34 @@ class BallRecords:
         return {self.first + i: (int(x), int(y), int(v)) for i, (x, y, v, p) in enumerate(self.data.tolist()) if p}
 
 
-def _yolo_records(results: list, tracker) -> YoloRecords:
+def _yolo_records(blocks: list, tracker) -> YoloRecords:
+    """This rank's frames (a list of per-batch ResultBlocks, or of Results) as one padded block."""
     kpt_shape = tracker.model.kpt_shape
+    if blocks and not isinstance(blocks[0], ResultBlock):  # plain Results: one frame each
+        rowlen = 6 + (kpt_shape[0] * kpt_shape[1] if kpt_shape else 0)
+        one = []
+        for r in blocks:
+            n = len(r.boxes)
+            rows = np.zeros((1, max(n, 1), rowlen), dtype=np.float32)
+            rows[0, :n, :6] = r.boxes.data.numpy()
+            if kpt_shape and n:
+                rows[0, :n, 6:] = r.keypoints.data.numpy().reshape(n, rowlen - 6)
+            one.append(ResultBlock(rows, np.array([n], dtype=np.int32), kpt_shape, r.names, r.orig_shape))
+        blocks = one
     rowlen = 6 + (kpt_shape[0] * kpt_shape[1] if kpt_shape else 0)
-    cap = max([len(r.boxes) for r in results], default=0)
-    rows = torch.zeros((len(results), max(cap, 1), rowlen), dtype=torch.float32)
-    counts = torch.zeros((len(results),), dtype=torch.int32)
-    for i, r in enumerate(results):
-        n = len(r.boxes)
-        counts[i] = n
-        if n:
-            rows[i, :n, :6] = r.boxes.data
-            if kpt_shape:
-                rows[i, :n, 6:] = r.keypoints.data.reshape(n, -1)
-    return YoloRecords(rows, counts, kpt_shape)
+    empty = ResultBlock(np.zeros((0, 1, rowlen), np.float32), np.zeros((0,), np.int32), kpt_shape, None, None)
+    blk = ResultBlock.concat(blocks, like=empty)
+    return YoloRecords(torch.from_numpy(blk.rows), torch.from_numpy(blk.counts), kpt_shape)
 
 
 def _ball_records(xyv: dict, lo: int, hi: int) -> BallRecords:
-    data = torch.zeros((hi - lo, 4), dtype=torch.int32)
-    for n, (x, y, v) in xyv.items():
-        if lo <= n < hi:
-            data[n - lo] = torch.tensor([x, y, v, 1], dtype=torch.int32)
-    return BallRecords(lo, data)
+    data = np.zeros((hi - lo, 4), dtype=np.int32)
+    own = [(n - lo, x, y, v) for n, (x, y, v) in xyv.items() if lo <= n < hi]
+    if own:
+        a = np.asarray(own, dtype=np.int64)
+        data[a[:, 0], :3] = a[:, 1:]
+        data[a[:, 0], 3] = 1
+    return BallRecords(lo, torch.from_numpy(data))
 
 
 def _comm_device() -> torch.device:

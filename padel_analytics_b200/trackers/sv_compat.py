@@ -452,6 +452,19 @@ class ByteTrack:
         out.tracker_id = ids[:n][keep].astype(int)
         return out
 
+    def update_many(self, xyxy: np.ndarray, scores: np.ndarray, counts: np.ndarray) -> np.ndarray:
+        """`len(counts)` consecutive frames in one native call: xyxy (total, 4) / scores (total) float32 are the frames'
+        detections back to back.  Returns the track id of every detection (-1 = no active track), exactly what
+        per-frame update_with_detections calls would assign."""
+        xyxy = np.ascontiguousarray(xyxy, dtype=np.float32).reshape(-1, 4)
+        scores = np.ascontiguousarray(scores, dtype=np.float32)
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        assert int(counts.sum()) == len(xyxy) == len(scores)
+        ids = np.empty(max(len(xyxy), 1), dtype=np.int32)
+        self._L.check(self._L.lib().pb_bytetrack_update_many(self._h, xyxy.ctypes.data, scores.ctypes.data,
+                                                             counts.ctypes.data, len(counts), ids.ctypes.data))
+        return ids[:len(xyxy)]
+
 
 if HAVE_SUPERVISION:  # pragma: no cover
     VideoInfo = _sv.VideoInfo  # noqa: F811

@@ -457,3 +457,72 @@ def test_native_bytetrack_equals_the_python_restatement():
             assert np.array_equal(o1.tracker_id, o2.tracker_id) and np.array_equal(o1.xyxy, o2.xyxy), (seed, frames)
             frames += 1
     assert frames == 1600
+
+
+def test_block_postprocess_equals_per_result_postprocess():
+    """The dense fast path (ResultBlock -> one polygon test, one pb_bytetrack_update_many call, vectorised ratios) must
+    produce exactly what the per-frame loop over ultralytics-style Results produces, for all three YOLO trackers."""
+    from types import SimpleNamespace
+
+    from padel_analytics_b200.engine.yolo_engine import ResultBlock
+    from padel_analytics_b200.trackers import sv_compat as sv
+    from padel_analytics_b200.trackers.keypoints_tracker import KeypointsTracker
+    from padel_analytics_b200.trackers.players_keypoints_tracker import PlayerKeypointsTracker
+    from padel_analytics_b200.trackers.players_tracker import PlayerTracker
+
+    rng = np.random.default_rng(11)
+    F, cap = 90, 7
+
+    def block(kpt_shape):
+        K, D = kpt_shape if kpt_shape else (0, 0)
+        rows = np.zeros((F, cap, 6 + K * D), np.float32)
+        counts = rng.integers(0, cap + 1, F).astype(np.int32)
+        counts[:3] = (0, 1, cap)
+        # four slowly moving boxes + noise so that ByteTrack keeps, loses and re-finds tracks
+        base = rng.uniform(100, 800, (cap, 2))
+        for f in range(F):
+            xy = base + 3.0 * f + rng.normal(0, 2, (cap, 2))
+            rows[f, :, 0:2] = xy
+            rows[f, :, 2:4] = xy + rng.uniform(40, 120, (cap, 2))
+            rows[f, :, 4] = np.sort(rng.uniform(0.05, 0.95, cap))[::-1]
+        if K:
+            rows[..., 6:] = rng.uniform(0, 640, (F, cap, K * D)).astype(np.float32)
+        rows[np.arange(cap)[None, :] >= counts[:, None]] = 0
+        return ResultBlock(rows, counts, kpt_shape, {0: "person"}, (1080, 1920))
+
+    def stub(cls, **attrs):
+        t = object.__new__(cls)
+        for k, v in attrs.items():
+            setattr(t, k, v)
+        return t
+
+    poly = np.array([[50, 50], [1500, 60], [1600, 1000], [40, 900]])
+    blk = block(None)
+    outs = []
+    for as_block in (True, False):
+        t = stub(PlayerTracker, polygon_zone=sv.PolygonZone(poly, frame_resolution_wh=(1920, 1080)),
+                 byte_track=sv.ByteTrack(frame_rate=30))
+        outs.append(t.postprocess(blk if as_block else list(blk)))
+    assert sum(len(p) for p in outs[0]) > F  # the scenario does track something
+    assert len(outs[0]) == len(outs[1]) == F
+    for a, b in zip(*outs):
+        assert [p.serialize() for p in a] == [p.serialize() for p in b]
+    # and split over several calls (the batches of a pass) == one call (rank 0 after the gather)
+    t = stub(PlayerTracker, polygon_zone=None, byte_track=sv.ByteTrack(frame_rate=30))
+    whole = t.postprocess(blk)
+    t = stub(PlayerTracker, polygon_zone=None, byte_track=sv.ByteTrack(frame_rate=30))
+    pieces = t.postprocess(blk[:32]) + t.postprocess(blk[32:64]) + t.postprocess(blk[64:])
+    assert [[p.serialize() for p in a] for a in whole] == [[p.serialize() for p in a] for a in pieces]
+
+    blk = block((13, 3))
+    t = stub(PlayerKeypointsTracker, train_image_size=1280)
+    a, b = t.postprocess(blk, (1080, 1920)), t.postprocess(list(blk), (1080, 1920))
+    assert [x.serialize() for x in a] == [x.serialize() for x in b]
+    blk = block((12, 3))
+    t = stub(KeypointsTracker)
+    a, b = t.postprocess(blk, (1080, 1920)), t.postprocess(list(blk), (1080, 1920))
+    assert [x.serialize() for x in a] == [x.serialize() for x in b]
+
+    # concat pads to the largest count and keeps frame order
+    c = ResultBlock.concat([blk[:10], blk[10:11], blk[11:]])
+    assert np.array_equal(c.counts, blk.counts) and np.array_equal(c.rows, blk.rows[:, :c.rows.shape[1]])
