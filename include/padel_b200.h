@@ -48,6 +48,12 @@ extern "C" {
                            MaxPool2d after each encoder block (models.py:60,62,64); 3x3 stride-1 convs only       */
 
 const char* pb_last_error(void);
+
+/* Options captured by the conv plans built AFTER this call (pb_program_add_conv, pb_conv2d): sm_limit > 0 sizes their
+ * persistent grids for that many SMs instead of the whole device (a program meant to run beside other streams leaves
+ * the remaining SMs to them); pdl = 1 / 0 turns programmatic dependent launch between consecutive kernels on / off for
+ * those plans, -1 = the process default (on, PADEL_B200_PDL=0 disables).  (0, -1) restores the defaults. */
+void pb_set_plan_options(int sm_limit, int pdl);
 int pb_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 long long pb_launch_count(void);

@@ -1,4 +1,5 @@
 // C-ABI surface of libpadel_b200.so: error reporting, programs (op lists), one-shot conv launches.
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -20,7 +21,15 @@ void set_error(const char* fmt, ...) {
   g_error = buf;
 }
 
-int num_sms() {
+static std::atomic<int> g_plan_sm_limit{0};
+static std::atomic<int> g_plan_pdl{-1};
+
+int plan_pdl() {
+  const int v = g_plan_pdl.load();
+  return v < 0 ? (pdl_enabled() ? 1 : 0) : (v != 0);
+}
+
+static int device_sms() {
   static int sms = 0;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -30,6 +39,12 @@ int num_sms() {
       sms = 148;
   });
   return sms;
+}
+
+// SMs a plan may size its persistent grid for: all of them, or the budget set by pb_set_plan_options
+int num_sms() {
+  const int lim = g_plan_sm_limit.load(), sms = device_sms();
+  return (lim > 0 && lim < sms) ? lim : sms;
 }
 
 int ensure_dynamic_smem(const void* func, size_t bytes) {
@@ -81,6 +96,11 @@ using namespace pb;
 extern "C" {
 
 const char* pb_last_error(void) { return g_error.c_str(); }
+
+void pb_set_plan_options(int sm_limit, int pdl) {
+  g_plan_sm_limit.store(sm_limit > 0 ? sm_limit : 0);
+  g_plan_pdl.store(pdl < 0 ? -1 : (pdl != 0));
+}
 int pb_version(void) { return 100; }
 long long pb_launch_count(void) { return g_launches.load(); }
 

@@ -780,7 +780,8 @@ int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
   HaloKernelFn fn = kp.pair ? halo_kernel_for<true>(kp.hs_S, kp.KB / 16) : halo_kernel_for<false>(kp.hs_S, kp.KB / 16);
   PB_CHECK(fn != nullptr, "conv(halo): no kernel instantiation for S=%d, k-steps=%d", kp.hs_S, kp.KB / 16);
   PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
-  cudaError_t le = launch_pdl(fn, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, kp.pair ? 2 : 1,
+  cudaError_t le = launch_ex(fn, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, kp.pair ? 2 : 1,
+                              plan->pdl != 0,
                               plan->tmap_a, plan->tmap_w, plan->kp);
   PB_CHECK(le == cudaSuccess,
            "conv(halo): launch failed: %s (pair %d, grid %d, threads %d, smem %zu, tiles %d, S %d, BN %d, KB %d)",

@@ -428,6 +428,7 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     kp.dbg_flags = df ? atoi(df) : 0;
   }
   plan->variant = 0;
+  plan->pdl = plan_pdl();
   if (stem) return conv_stem_setup(d, plan, encode);
   {
     // halo variant for 3x3/s1 layers: default on for cout <= 192 (the layers the per-tap kernel leaves
@@ -572,7 +573,8 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
   if (plan->variant == 1) return conv_halo_launch(plan, stream);
   PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(conv_tc_kernel), 227 * 1024));
-  PB_CUDA(launch_pdl(conv_tc_kernel, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, 1, plan->tmap_a,
+  PB_CUDA(launch_ex(conv_tc_kernel, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, 1, plan->pdl != 0,
+                    plan->tmap_a,
                      plan->tmap_w, plan->kp));
   count_launch();
   return 0;

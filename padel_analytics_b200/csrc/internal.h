@@ -23,13 +23,14 @@ int num_sms();
 int ensure_dynamic_smem(const void* func, size_t bytes);
 // Programmatic dependent launch for the kernels of a program (PADEL_B200_PDL=0 disables; default on)
 bool pdl_enabled();
+int plan_pdl();  // the value a plan built now captures
 
 #ifdef __CUDACC__
 // Launch `kernel` with the programmatic-stream-serialization attribute (see ptx.cuh::griddep_wait): only for kernels
 // that call griddep_wait() before touching data another kernel may have written / may still be reading.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                              int cluster, Args... args) {
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             int cluster, bool pdl, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -44,7 +45,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl_enabled()) {
+  if (pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -53,6 +54,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.numAttrs = (unsigned)na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
   return e == cudaSuccess ? cudaGetLastError() : e;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster, Args... args) {
+  return launch_ex(kernel, grid, block, smem, stream, cluster, pdl_enabled(), args...);
 }
 #endif
 
@@ -169,6 +176,7 @@ struct ConvPlan {
   int threads;
   size_t smem_bytes;
   int variant;  // 0 = per-tap boxes (conv_tc_kernel), 1 = shared halo tile (conv_halo_kernel)
+  int pdl;      // programmatic dependent launch for this plan (captured from pb_set_plan_options at build time)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

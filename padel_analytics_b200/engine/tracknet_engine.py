@@ -95,6 +95,18 @@ class TrackNetEngine:
         self.pred = torch.zeros((7 + B, 8, H, W), dtype=torch.float32, device=dev)
 
     def _build(self):
+        # PADEL_B200_BALL_SMS=n: size this program's persistent grids for n SMs (and launch its kernels without
+        # programmatic overlap, so a waiting successor never parks on the SMs left free) -- for running beside the YOLO
+        # chains of the other trackers (FusedPass streams mode 2) instead of before / after them
+        sms = int(os.environ.get("PADEL_B200_BALL_SMS", "0"))
+        if sms > 0:
+            L.lib().pb_set_plan_options(sms, 0)
+        try:
+            self._build_program()
+        finally:
+            L.lib().pb_set_plan_options(0, -1)
+
+    def _build_program(self):
         P = ops.Program()
         W_ = self._w
         R, UP, SIG = L.ACT_RELU, L.OUT_F16_NHWC_UP2, L.ACT_SIGMOID

@@ -53,7 +53,10 @@ class FusedPass:
         self.trackers = trackers
         self.raw = raw
         self.mode = int(os.environ.get("PADEL_B200_STREAMS", "1")) if streams is None else streams
-        self.side = {name: torch.cuda.Stream() for name in trackers}
+        # side streams: the YOLO chains at high priority (their CTAs are placed first whenever SMs free up), the ball
+        # tracker (mode 2 only) at normal priority
+        self.side = {name: torch.cuda.Stream(priority=0 if isinstance(t, BallTracker) else -1)
+                     for name, t in trackers.items()}
         self.hw = tuple(frame_hw)
         self.B = batch_size
         self.dev = torch.device("cuda")
