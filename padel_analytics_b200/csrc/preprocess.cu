@@ -112,6 +112,84 @@ pil_horizontal_kernel(const uint8_t* __restrict__ src, int Ws, uint8_t* __restri
   }
 }
 
+// Horizontal, R source rows per CTA (the product path when Ws % 16 == 0): the same arithmetic, organised so that
+// a thread computes output column xo for R rows with ONE read of its window bounds and filter taps, rows are packed to
+// one 32-bit word per pixel straight from 16-byte global loads (48 bytes = 16 pixels per step, no byte-wise staging),
+// and the R output rows -- contiguous in `tmp` -- leave through shared memory as 16-byte stores.  The one-row kernel
+// above spends ~12 instructions per row and tap (it is instruction-bound: 175 us for 32 x 1080p -> 1280 columns,
+// 5 x its HBM time); this one ~8, and the byte-wise stage / pack / scattered byte stores are gone.
+template <int R>
+__global__ void __launch_bounds__(256)
+pil_horizontal_rows_kernel(const uint8_t* __restrict__ src, int Ws, long rows_total, uint8_t* __restrict__ tmp, int Wo,
+                           const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, int swap_rb) {
+  extern __shared__ __align__(16) uint8_t hrow[];  // [R][Ws] uint32 pixels | [R][Wo*3] output bytes
+  uint32_t* packed = reinterpret_cast<uint32_t*>(hrow);
+  uint8_t* stage = hrow + (size_t)R * Ws * 4;
+  const long row0 = (long)blockIdx.x * R;
+  const int rows = (int)(rows_total - row0 < R ? rows_total - row0 : R);
+  const int groups = Ws / 16;  // 16 pixels = 48 bytes = three 16-byte loads
+  for (int i = threadIdx.x; i < rows * groups; i += blockDim.x) {
+    const int r = i / groups, g = i - r * groups;
+    const uint4* gp = reinterpret_cast<const uint4*>(src + (row0 + r) * (size_t)Ws * 3) + 3 * g;
+    const uint4 a = __ldg(gp), b = __ldg(gp + 1), c = __ldg(gp + 2);
+    const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    uint32_t px[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // 4 pixels per 3 words; the top byte of a packed pixel is never read
+      px[4 * q + 0] = w[3 * q];
+      px[4 * q + 1] = __byte_perm(w[3 * q], w[3 * q + 1], 0x0543);
+      px[4 * q + 2] = __byte_perm(w[3 * q + 1], w[3 * q + 2], 0x0432);
+      px[4 * q + 3] = w[3 * q + 2] >> 8;
+    }
+    uint4* pp = reinterpret_cast<uint4*>(packed + (size_t)r * Ws + 16 * g);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pp[q] = make_uint4(px[4 * q], px[4 * q + 1], px[4 * q + 2], px[4 * q + 3]);
+  }
+  __syncthreads();
+  const int orow = Wo * 3;
+  for (int xo = threadIdx.x; xo < Wo; xo += blockDim.x) {
+    const int xmin = bounds[2 * xo], xs = bounds[2 * xo + 1];
+    const int* k = kk + (size_t)xo * ksize;
+    const uint32_t* p = packed + xmin;
+    int s[R][3];
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[r][0] = s[r][1] = s[r][2] = 1 << 21;
+#pragma unroll 2
+    for (int x = 0; x < xs; ++x) {
+      const int kv = __ldg(k + x);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint32_t v = p[(size_t)r * Ws + x];
+        s[r][0] += (int)(v & 0xFF) * kv;
+        s[r][1] += (int)((v >> 8) & 0xFF) * kv;
+        s[r][2] += (int)((v >> 16) & 0xFF) * kv;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint8_t v0 = (uint8_t)min(max(s[r][0] >> 22, 0), 255);
+      const uint8_t v1 = (uint8_t)min(max(s[r][1] >> 22, 0), 255);
+      const uint8_t v2 = (uint8_t)min(max(s[r][2] >> 22, 0), 255);
+      uint8_t* o = stage + (size_t)r * orow + 3 * xo;
+      o[0] = swap_rb ? v2 : v0;
+      o[1] = v1;
+      o[2] = swap_rb ? v0 : v2;
+    }
+  }
+  __syncthreads();
+  // rows row0 .. row0+rows-1 of `tmp` are one contiguous run of rows * Wo * 3 bytes (Wo % 4 == 0 -> 4-byte multiples;
+  // 16-byte vectors when the run starts on a 16-byte boundary, i.e. (R * Wo * 3) % 16 == 0)
+  uint8_t* o = tmp + (size_t)row0 * orow;
+  const int nbytes = rows * orow;
+  if ((reinterpret_cast<uintptr_t>(o) & 15) == 0 && (nbytes & 15) == 0) {
+    for (int i = threadIdx.x; i < nbytes / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(o)[i] = reinterpret_cast<const uint4*>(stage)[i];
+  } else {
+    for (int i = threadIdx.x; i < nbytes / 4; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(o)[i] = reinterpret_cast<const uint32_t*>(stage)[i];
+  }
+}
+
 // Vertical: one thread per 4 output pixels (12 bytes = three 32-bit words per tap row).  Writes the uint8 result
 // and/or the normalised fp16 network input directly (f16_layout 0: NHWC16, 1: PB_IN_STEM4 padded 4-channel).
 __global__ void pil_vertical_kernel(const uint8_t* __restrict__ tmp, int B, int Hs, int Wo, uint8_t* __restrict__ dst,
@@ -268,8 +346,29 @@ int pb_pil_resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* tmp, ui
   PB_CHECK(f16_layout >= 0 && f16_layout <= 2, "pil_resize: bad f16_layout");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t hsmem = (((size_t)Ws * 3 + 15) & ~(size_t)15) + (size_t)Ws * 4;
-  PB_CHECK(hsmem <= 48 * 1024, "pil_resize: source rows of %d pixels do not fit the row buffer", Ws);
-  pil_horizontal_kernel<<<B * Hs, 256, hsmem, s>>>(src, Ws, tmp, Wo, bounds_h, kk_h, ksize_h, swap_rb);
+  // R rows per CTA when the source rows are whole 48-byte groups (every video format in practice); PADEL_B200_PIL_ROWS=1
+  // selects the one-row kernel (A/B)
+  static const int rows_env = [] {
+    const char* e = getenv("PADEL_B200_PIL_ROWS");
+    return e ? atoi(e) : 4;
+  }();
+  const long rows_total = (long)B * Hs;
+  const size_t smem4 = (size_t)4 * Ws * 4 + (size_t)4 * Wo * 3;
+  const size_t smem2 = (size_t)2 * Ws * 4 + (size_t)2 * Wo * 3;
+  if (rows_env >= 2 && Ws % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && smem2 <= 200 * 1024) {
+    if (rows_env >= 4 && smem4 <= 100 * 1024) {
+      PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(&pil_horizontal_rows_kernel<4>), smem4));
+      pil_horizontal_rows_kernel<4><<<(unsigned)((rows_total + 3) / 4), 256, smem4, s>>>(src, Ws, rows_total, tmp, Wo,
+                                                                                         bounds_h, kk_h, ksize_h, swap_rb);
+    } else {
+      PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(&pil_horizontal_rows_kernel<2>), smem2));
+      pil_horizontal_rows_kernel<2><<<(unsigned)((rows_total + 1) / 2), 256, smem2, s>>>(src, Ws, rows_total, tmp, Wo,
+                                                                                         bounds_h, kk_h, ksize_h, swap_rb);
+    }
+  } else {
+    PB_CHECK(hsmem <= 48 * 1024, "pil_resize: source rows of %d pixels do not fit the row buffer", Ws);
+    pil_horizontal_kernel<<<B * Hs, 256, hsmem, s>>>(src, Ws, tmp, Wo, bounds_h, kk_h, ksize_h, swap_rb);
+  }
   PB_CUDA(cudaGetLastError());
   const long t2 = (long)B * Ho * (Wo / 4);
   pil_vertical_kernel<<<grid_for(t2, 256), 256, 0, s>>>(tmp, B, Hs, Wo, dst, Ho, bounds_v, kk_v, ksize_v,

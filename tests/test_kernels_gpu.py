@@ -54,8 +54,10 @@ def test_letterbox_bit_exact(hw):
 
 
 @pytest.mark.parametrize("size", [(512, 288), (1280, 1280), (640, 640)])
-@pytest.mark.parametrize("hw", [(1080, 1920), (2160, 3840)])
+@pytest.mark.parametrize("hw", [(1080, 1920), (2160, 3840), (542, 954), (1081, 1936)])
 def test_pil_resize_bit_exact(size, hw):
+    """(1080, 1920) / (2160, 3840) / (1081, 1936: odd row count) take the multi-row horizontal kernel (4 and 2 rows per
+    CTA), width 954 (not a multiple of 16) the one-row kernel."""
     fr = _frames(2, *hw, seed=1)
     Wo, Ho = size
     bh, kh, ksh = resample.pil_bicubic_tables(hw[1], Wo)
