@@ -294,14 +294,31 @@ __device__ __forceinline__ void epi_chunk(int act, int has_res, bool plain_silu,
 // `sub_res` BYTES / halves apart in the output / residual tensors), `nch` 16-column chunks each (`cout_n` channels of
 // this N tile exist).  valid_mask bit j = the thread's pixel of sub-tile j exists.  op0 / rp0 point at channel 0 of
 // this N tile.  Software pipeline: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed.
-__device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOut& eo, uint32_t t_addr0, int S,
+// kEpi (a kernel template parameter, chosen per plan by the host -- conv_epi_class): 0 = every case at run time;
+// PB_EPI_SILU / PB_EPI_RELU = the plain case (that activation, no residual, fp16 NHWC store, no secondary output),
+// PB_EPI_SILU_RES = SiLU then the shortcut add, PB_EPI_F32 = the linear fp32 head outputs, with everything folded at
+// compile time.  The epilogue warps of the light layers are issue-latency-bound (two epilogue warps
+// per SM sub-partition; profiles/r02_epilogue_stalls.md) and the run-time form spends 14 of its ~285 instructions per
+// chunk on CTA-uniform branches.  One epilogue per kernel instantiation: a kernel holding several copies exceeds the
+// 128-register budget and spills (measured; same note).
+template <int kEpi>
+__device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOut& eo_in, uint32_t t_addr0, int S,
                                               uint32_t sub_cols, int nch, int cout_n, const float* __restrict__ sbias,
                                               char* op0, const __half* rp0, size_t sub_out, size_t sub_res,
                                               uint32_t valid_mask, char* op20 = nullptr, size_t sub_out2 = 0) {
   uint32_t ra[16], rb[16];
-  const int act = kp.act;
-  const int has_res = kp.res != nullptr ? (kp.res_first ? 2 : 1) : 0;
-  const bool plain_silu = (kp.dbg_flags & 1) != 0;
+  constexpr bool kSpec = kEpi != PB_EPI_GENERIC;
+  EpiOut eo = eo_in;
+  if (kSpec) {
+    eo.mode = kEpi == PB_EPI_F32 ? PB_OUT_F32_NHWC : PB_OUT_F16_NHWC;
+    eo.mode2 = PB_OUT2_NONE;
+  }
+  const int act = (kEpi == PB_EPI_SILU || kEpi == PB_EPI_SILU_RES) ? PB_ACT_SILU
+                  : kEpi == PB_EPI_RELU                            ? PB_ACT_RELU
+                  : kEpi == PB_EPI_F32                             ? PB_ACT_NONE
+                                                                   : kp.act;
+  const int has_res = kEpi == PB_EPI_SILU_RES ? 1 : kSpec ? 0 : (kp.res != nullptr ? (kp.res_first ? 2 : 1) : 0);
+  const bool plain_silu = kSpec ? false : (kp.dbg_flags & 1) != 0;
   const int cbytes = eo.mode == PB_OUT_F32_NHWC ? 64 : 32;  // bytes of one 16-channel chunk in the output
   int j = 0, c = 0;
   tmem_ld16(t_addr0, ra);

@@ -61,7 +61,7 @@ __device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t row_b
 // cluster of two, so the single-CTA and the CTA-pair variants are separate instantiations.
 // kS (sub-tiles) and kSteps (16-element k-steps per channel block) are compile-time so the UMMA issue
 // loop is straight-line code with immediate descriptor offsets.
-template <bool kPair, int kS, int kSteps>
+template <bool kPair, int kS, int kSteps, int kEpi>
 __global__ void __launch_bounds__(kConvMaxThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ ConvKParams kp) {
@@ -277,7 +277,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const int row = m >> 3, col = m & 7;
-    const bool fast = epilogue_fast_ok(kp);
+    const bool fast = kEpi != PB_EPI_GENERIC || epilogue_fast_ok(kp);  // the host picks a plain class only when it holds
     int seq = egroup, acc = egroup;  // sequence number / accumulator stage / phase by counters (egroups <= acc_stages)
     uint32_t acc_ph = 0;
     for (int tile = cta0 + egroup * cstride; egroup < kp.egroups && tile < kp.total_tiles;
@@ -327,10 +327,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * kp.acc_cols);
         char* obase = reinterpret_cast<char*>(kp.out) + opix * pxb + (size_t)kp.out_coff * esz;
-          epilogue_fast(kp, eo, t0, S, (uint32_t)kp.acc_cols, (kp.cout_store + 15) >> 4, kp.cout_store, tail->bias,
+          epilogue_fast<kEpi>(kp, eo, t0, S, (uint32_t)kp.acc_cols, (kp.cout_store + 15) >> 4, kp.cout_store, tail->bias,
                         obase, kp.res + pix0 * kp.res_C + kp.res_coff, sub_out, (size_t)8 * kp.res_C, vm, obase2,
                         sub_out2);
-      } else
+      } else if constexpr (kEpi == PB_EPI_GENERIC)
       for (int j = 0; j < S; ++j) {
         EpiPix px;
         px.n = t.n;
@@ -764,10 +764,10 @@ int conv_halo_s2_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn enco
 
 typedef void (*HaloKernelFn)(CUtensorMap, CUtensorMap, ConvKParams);
 
-template <bool kPair>
+template <bool kPair, int kEpi>
 static HaloKernelFn halo_kernel_for(int S, int steps) {
 #define PB_HALO_CASE(s_, k_) \
-  if (S == s_ && steps == k_) return conv_halo_kernel<kPair, s_, k_>;
+  if (S == s_ && steps == k_) return conv_halo_kernel<kPair, s_, k_, kEpi>;
   PB_HALO_CASE(1, 1) PB_HALO_CASE(1, 2) PB_HALO_CASE(1, 4)
   PB_HALO_CASE(2, 1) PB_HALO_CASE(2, 2) PB_HALO_CASE(2, 4)
   PB_HALO_CASE(4, 1) PB_HALO_CASE(4, 2) PB_HALO_CASE(4, 4)
@@ -775,9 +775,20 @@ static HaloKernelFn halo_kernel_for(int S, int steps) {
   return nullptr;
 }
 
+// CTA-pair layers are deep (cin >= 128) and tensor-bound: the run-time epilogue only
+static HaloKernelFn halo_kernel_pick(const ConvPlan* plan) {
+  const ConvKParams& kp = plan->kp;
+  const int S = kp.hs_S, steps = kp.KB / 16;
+  if (kp.pair) return halo_kernel_for<true, PB_EPI_GENERIC>(S, steps);
+  if (plan->epi == PB_EPI_SILU) return halo_kernel_for<false, PB_EPI_SILU>(S, steps);
+  if (plan->epi == PB_EPI_RELU) return halo_kernel_for<false, PB_EPI_RELU>(S, steps);
+  if (plan->epi == PB_EPI_SILU_RES) return halo_kernel_for<false, PB_EPI_SILU_RES>(S, steps);
+  return halo_kernel_for<false, PB_EPI_GENERIC>(S, steps);
+}
+
 int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream) {
   const ConvKParams& kp = plan->kp;
-  HaloKernelFn fn = kp.pair ? halo_kernel_for<true>(kp.hs_S, kp.KB / 16) : halo_kernel_for<false>(kp.hs_S, kp.KB / 16);
+  HaloKernelFn fn = halo_kernel_pick(plan);
   PB_CHECK(fn != nullptr, "conv(halo): no kernel instantiation for S=%d, k-steps=%d", kp.hs_S, kp.KB / 16);
   PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
   cudaError_t le = launch_ex(fn, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, kp.pair ? 2 : 1,

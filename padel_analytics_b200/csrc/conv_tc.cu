@@ -48,6 +48,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& kp, int tile
   return c;
 }
 
+template <int kEpi>
 __global__ void __launch_bounds__(kConvMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ ConvKParams kp) {
@@ -209,7 +210,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int tw_i = p & TWm;
     const int th_i = (p >> kp.tw_log2) & THm;
     const int tn_i = p >> (kp.tw_log2 + kp.th_log2);
-    const bool fast = epilogue_fast_ok(kp);
+    const bool fast = kEpi != PB_EPI_GENERIC || epilogue_fast_ok(kp);  // the host picks a plain class only when it holds
     // per-CTA tile sequence number / accumulator stage / phase advance by counters (egroups <= acc_stages)
     int seq = egroup, acc = egroup;
     uint32_t acc_phase = 0;
@@ -258,10 +259,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             eo.dy2 = (size_t)(2 * kp.Wo) * pxb2;
             obase2 = reinterpret_cast<char*>(kp.out2) + pix2 * pxb2 + (size_t)(kp.out2_coff + tc.nt * kp.BN) * 2;
           }
-            epilogue_fast(kp, eo, t_addr, 1, 0u, (cn + 15) >> 4, cn, sb, obase, rbase, 0, 0, px.valid ? 1u : 0u, obase2,
-                          0);
+            epilogue_fast<kEpi>(kp, eo, t_addr, 1, 0u, (cn + 15) >> 4, cn, sb, obase, rbase, 0, 0, px.valid ? 1u : 0u,
+                                obase2, 0);
         }
-      } else
+      } else if constexpr (kEpi == PB_EPI_GENERIC) {
       for (int c = 0; c < kp.BN; c += 32) {
         // two 16-column TMEM loads in flight, one wait
         uint32_t r0[16], r1[16];
@@ -282,6 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                      (kp.res && kp.res_first) ? kp.res + px.pix * kp.res_C + kp.res_coff + ch0 + 16 : nullptr);
           epilogue_store16(kp, px, ch0 + 16, c + 16, v, hacc);
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -339,6 +341,29 @@ extern "C" void pb_debug_conv_timeline(long long* buf) { g_conv_dbg = buf; }
 #else
 static long long* const g_conv_dbg = nullptr;
 #endif
+
+// Which epilogue instantiation a layer runs: a plain class when the vectorised epilogue applies (the conditions of
+// epilogue_fast_ok) and the layer is activation-only -- no residual, fp16 NHWC store, no secondary output, no fused head.
+// PADEL_B200_CONV_EPI=0 keeps every layer on the run-time epilogue (A/B).
+int conv_epi_class(const pb_conv_desc* d, const ConvKParams& kp) {
+  static const int enabled = [] {
+    const char* e = getenv("PADEL_B200_CONV_EPI");
+    return e ? atoi(e) : 1;
+  }();
+  if (!enabled || kp.dbg_flags != 0 || kp.dbg != nullptr) return PB_EPI_GENERIC;
+  if (d->head_n != 0 || d->out2_mode != PB_OUT2_NONE || (reinterpret_cast<uintptr_t>(d->out) & 31) != 0)
+    return PB_EPI_GENERIC;
+  if (d->out_mode == PB_OUT_F32_NHWC) {  // 32-byte aligned 8-float groups
+    return (!d->res && d->act == PB_ACT_NONE && ((d->out_C | d->out_coff) & 7) == 0 && d->ksize == 1) ? PB_EPI_F32
+                                                                                                       : PB_EPI_GENERIC;
+  }
+  if (d->out_mode != PB_OUT_F16_NHWC || ((d->out_C | d->out_coff | d->cout_store) & 15) != 0) return PB_EPI_GENERIC;
+  if (d->res) {
+    const bool ok = !d->res_before_act && d->act == PB_ACT_SILU && ((d->res_C | d->res_coff) & 7) == 0;
+    return ok ? PB_EPI_SILU_RES : PB_EPI_GENERIC;
+  }
+  return d->act == PB_ACT_SILU ? PB_EPI_SILU : (d->act == PB_ACT_RELU ? PB_EPI_RELU : PB_EPI_GENERIC);
+}
 
 static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
   PB_CHECK(d && plan, "conv: null argument");
@@ -429,6 +454,7 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
   }
   plan->variant = 0;
   plan->pdl = plan_pdl();
+  plan->epi = conv_epi_class(d, kp);
   if (stem) return conv_stem_setup(d, plan, encode);
   {
     // halo variant for 3x3/s1 layers: default on for cout <= 192 (the layers the per-tap kernel leaves
@@ -572,10 +598,15 @@ int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan) {
 
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
   if (plan->variant == 1) return conv_halo_launch(plan, stream);
-  PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(conv_tc_kernel), 227 * 1024));
-  PB_CUDA(launch_ex(conv_tc_kernel, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, 1, plan->pdl != 0,
-                    plan->tmap_a,
-                     plan->tmap_w, plan->kp));
+  typedef void (*TcKernelFn)(CUtensorMap, CUtensorMap, ConvKParams);
+  const TcKernelFn fn = plan->epi == PB_EPI_SILU       ? conv_tc_kernel<PB_EPI_SILU>
+                        : plan->epi == PB_EPI_RELU     ? conv_tc_kernel<PB_EPI_RELU>
+                        : plan->epi == PB_EPI_SILU_RES ? conv_tc_kernel<PB_EPI_SILU_RES>
+                        : plan->epi == PB_EPI_F32      ? conv_tc_kernel<PB_EPI_F32>
+                                                       : conv_tc_kernel<PB_EPI_GENERIC>;
+  PB_CUDA((cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
+  PB_CUDA(launch_ex(fn, dim3(plan->grid), dim3(plan->threads), plan->smem_bytes, stream, 1, plan->pdl != 0, plan->tmap_a,
+                    plan->tmap_w, plan->kp));
   count_launch();
   return 0;
 }

@@ -177,7 +177,16 @@ struct ConvPlan {
   size_t smem_bytes;
   int variant;  // 0 = per-tap boxes (conv_tc_kernel), 1 = shared halo tile (conv_halo_kernel)
   int pdl;      // programmatic dependent launch for this plan (captured from pb_set_plan_options at build time)
+  int epi;      // PB_EPI_*: which epilogue instantiation of the kernel this layer runs
 };
+
+// epilogue classes (kernel template parameter kEpi)
+#define PB_EPI_GENERIC 0
+#define PB_EPI_SILU 1
+#define PB_EPI_RELU 2
+#define PB_EPI_SILU_RES 3  // SiLU, then + residual (ultralytics Bottleneck shortcut), fp16 NHWC
+#define PB_EPI_F32 4       // no activation, fp32 NHWC slice (YOLO head outputs)
+int conv_epi_class(const pb_conv_desc* d, const ConvKParams& kp);
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
