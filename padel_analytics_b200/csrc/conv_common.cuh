@@ -233,7 +233,7 @@ __device__ __forceinline__ void epi_compute16(int act, int has_res, bool plain_s
 
 __device__ __forceinline__ void epi_chunk(int act, int has_res, bool plain_silu, const EpiOut& eo, uint32_t (&r)[16],
                                           const float* __restrict__ sbias, char* op, const uint4 (&rv)[2], bool valid,
-                                          int nvalid, char* op2 = nullptr) {
+                                          int nvalid, char* op2 = nullptr, bool vec_tail = false) {
   float v[16];
   epi_compute16(act, has_res, plain_silu, r, sbias, rv, v);
   if (eo.mode == PB_OUT_F32_NHWC) {
@@ -246,11 +246,17 @@ __device__ __forceinline__ void epi_chunk(int act, int has_res, bool plain_silu,
                           __float_as_uint(v[4 * q + 3]));
       st_global_256(op, w[0], w[1]);
       st_global_256(op + 32, w[2], w[3]);
-    } else {
+    } else {  // the N tile ends inside this chunk: one 32-byte store if at least 8 floats exist, scalars for the rest
       float* o = reinterpret_cast<float*>(op);
+      int j0 = 0;
+      if (vec_tail && nvalid >= 8) {
+        st_global_256(op, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])),
+                      make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+        j0 = 8;
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if (j < nvalid) o[j] = v[j];
+        if (j >= j0 && j < nvalid) o[j] = v[j];
     }
     return;
   }
@@ -322,7 +328,16 @@ __device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOu
   const int cbytes = eo.mode == PB_OUT_F32_NHWC ? 64 : 32;  // bytes of one 16-channel chunk in the output
   int j = 0, c = 0;
   tmem_ld16(t_addr0, ra);
-#define PB_EPI_STAGE(cur, nxt)                                                                          \
+  // the shortcut operand is fetched one chunk ahead, like the accumulator: a global load issued and consumed inside
+  // the same chunk would put its whole latency on the chunk's critical path
+  constexpr bool kPrefetchRes = kEpi == PB_EPI_SILU_RES;  // (the run-time epilogue has no registers to spare for it)
+  uint4 rva[2] = {}, rvb[2] = {};
+  if (kPrefetchRes && (valid_mask & 1u)) {
+    const uint4* rp = reinterpret_cast<const uint4*>(rp0);
+    rva[0] = __ldg(rp);
+    rva[1] = __ldg(rp + 1);
+  }
+#define PB_EPI_STAGE(cur, nxt, rvc, rvn)                                                                \
   {                                                                                                     \
     int jn = j, cn = c + 1;                                                                             \
     if (cn == nch) {                                                                                    \
@@ -331,23 +346,30 @@ __device__ __forceinline__ void epilogue_fast(const ConvKParams& kp, const EpiOu
     }                                                                                                   \
     const bool more = jn < S;                                                                           \
     const bool valid = ((valid_mask >> j) & 1u) != 0;                                                   \
-    uint4 rv[2] = {};                                                                                   \
-    if (has_res && valid) { /* consumed after the activation math of this chunk */                      \
+    if (kPrefetchRes) {                                                                                 \
+      if (more && ((valid_mask >> jn) & 1u)) {                                                          \
+        const uint4* rp = reinterpret_cast<const uint4*>(rp0 + (size_t)jn * sub_res + cn * 16);         \
+        rvn[0] = __ldg(rp);                                                                             \
+        rvn[1] = __ldg(rp + 1);                                                                         \
+      }                                                                                                 \
+    }                                                                                                   \
+    uint4 rvl[2] = {};                                                                                  \
+    if (!kPrefetchRes && has_res && valid) { /* consumed after the activation math of this chunk */     \
       const uint4* rp = reinterpret_cast<const uint4*>(rp0 + (size_t)j * sub_res + c * 16);             \
-      rv[0] = __ldg(rp);                                                                                \
-      rv[1] = __ldg(rp + 1);                                                                            \
+      rvl[0] = __ldg(rp);                                                                               \
+      rvl[1] = __ldg(rp + 1);                                                                           \
     }                                                                                                   \
     tmem_ld_wait16(cur);                                                                                \
     if (more) tmem_ld16(t_addr0 + (uint32_t)jn * sub_cols + (uint32_t)(cn * 16), nxt);                  \
-    epi_chunk(act, has_res, plain_silu, eo, cur, sbias + c * 16, op0 + (size_t)j * sub_out + (size_t)(c * cbytes), rv, valid, \
-              cout_n - c * 16, op20 + (size_t)j * sub_out2 + (size_t)(c * 32));                          \
+    epi_chunk(act, has_res, plain_silu, eo, cur, sbias + c * 16, op0 + (size_t)j * sub_out + (size_t)(c * cbytes), kPrefetchRes ? rvc : rvl, valid, \
+              cout_n - c * 16, op20 + (size_t)j * sub_out2 + (size_t)(c * 32), kEpi == PB_EPI_F32);      \
     if (!more) break;                                                                                   \
     j = jn;                                                                                             \
     c = cn;                                                                                             \
   }
   for (;;) {
-    PB_EPI_STAGE(ra, rb)
-    PB_EPI_STAGE(rb, ra)
+    PB_EPI_STAGE(ra, rb, rva, rvb)
+    PB_EPI_STAGE(rb, ra, rvb, rva)
   }
 #undef PB_EPI_STAGE
 }

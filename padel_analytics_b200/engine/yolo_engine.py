@@ -323,7 +323,10 @@ class YoloEngine:
                 t2 = buf(h, w_, cm)
                 conv(t1m, sum(widths[:bi]), cm, f"{pre}.1", t2, 0, 3, 1)
                 w, b = self._wb(f"{pre}.2", cm, ops.pad16(cout_real), bn=False)
-                P.conv(ops.make_conv_desc(t2, 0, cm, w, b, 1, 1, L.ACT_NONE, feat, off, L.OUT_F32_NHWC, cout_real),
+                # whole 8-float groups are stored (one 32-byte store each): the slice of every branch is padded to a
+                # multiple of 8 channels in `feat`, and the padding channels have zero weights and bias
+                store = min((cout_real + 7) // 8 * 8, ops.pad16(cout_real))
+                P.conv(ops.make_conv_desc(t2, 0, cm, w, b, 1, 1, L.ACT_NONE, feat, off, L.OUT_F32_NHWC, store),
                        cin_real=self.sd[f"{pre}.2.weight"].shape[1], cout_real=cout_real)
             feats.append(feat)
             levels.append((feat, h, w_, st))
