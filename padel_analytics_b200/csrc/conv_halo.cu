@@ -51,10 +51,14 @@ __device__ __forceinline__ HaloTile halo_decode(const ConvKParams& kp, int tile,
   return t;
 }
 
-__device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes) {
-  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
-         (layout << 61);
+// row_bytes 128 / 64 / 32: the swizzled K-major layouts.  row_bytes 16: the un-swizzled K-major layout -- 8-row core
+// matrices of 16-byte rows at a 16-byte pitch, 8-row groups `sbo_bytes` apart, the second 16-byte half of a K = 16 row
+// `lbo_bytes` further (16: the row that follows -- overlapping rows, used by the stem's raw-pixel operand).
+__device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes,
+                                                  uint32_t lbo_bytes = 16) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : (row_bytes == 32 ? 6ull : 0ull));
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (layout << 61);
 }
 
 // kPair is a compile-time switch: a kernel that contains cta_group::2 instructions can only be launched as a
@@ -219,7 +223,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (dbg) bwait += clock64() - ta;
           // Descriptor arithmetic is hoisted: per (channel block, weight stage) one base descriptor each; taps,
           // sub-tiles and k-steps only add precomputed 16-byte-unit offsets to the low word.
-          const uint64_t a_desc0 = umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), a_row_bytes, sbo);
+          const uint64_t a_desc0 = (kp.dbg_flags & 8)  // bring-up: LBO / SBO roles swapped
+                                       ? umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), a_row_bytes, 16, sbo)
+                                       : umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), a_row_bytes, sbo);
           for (int tg = 0; tg < tap_groups; ++tg) {
             const long long tb = dbg ? clock64() : 0;
             mbar_wait(&tail->b_full[bst], kp.b_resident ? 0u : bph);  // resident: filled once, phase 0 stays complete
@@ -462,6 +468,24 @@ int conv_stem_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   kp.n_ntiles = 1;
   kp.halo_bytes = 16u * 3u * (uint32_t)(8 * S) * 32u;
   kp.hs_a_row_bytes = 32u;
+  // Raw-pixel operand (default; PADEL_B200_STEM_RAW=0 selects the overlapping-row box above): the tile's input region --
+  // 34 rows x (16 S + 2) pixels of 8 bytes, every byte once -- is one dense TMA box, and the UMMA descriptor reads the
+  // im2col rows out of it: output pixel ow's K = 16 row (pixels 2ow .. 2ow+3) starts 16 bytes after its neighbour's, so
+  // in the un-swizzled K-major layout (16-byte rows at a 16-byte pitch, second half of a row LBO = 16 bytes on) the
+  // overlapping rows ARE the canonical core matrix; the next output row is two image rows further (SBO), filter row r
+  // one image row (descriptor offset).  A third of the L2->SM traffic and of the shared memory of the box-per-row form.
+  const uint32_t pairs = (uint32_t)(8 * S) + 1;  // pixel pairs (16 bytes) per image row of the region
+  const uint32_t pitch = pairs * 16u;
+  static const int raw = [] {
+    const char* e = getenv("PADEL_B200_STEM_RAW");
+    return e ? atoi(e) : 1;
+  }();
+  if (raw) {
+    kp.halo_bytes = 17u * 2u * pitch;  // 17 row pairs (2 * 16 + 1 rows are read, the 34th is never addressed)
+    kp.hs_a_row_bytes = 16u;
+    kp.hs_sbo_rows = (int)(2u * pitch / 16u);  // x hs_a_row_bytes = 2 image rows
+    for (int r = 0; r < 3; ++r) kp.hs_tap_desc[r] = (int)(((uint32_t)r * pitch) >> 4);
+  }
   kp.a_bytes = (kp.halo_bytes + 1023u) & ~1023u;
   kp.b_tx_bytes = 3u * (uint32_t)BN * 32u;
   kp.b_bytes = (kp.b_tx_bytes + 1023u) & ~1023u;
@@ -486,9 +510,19 @@ int conv_stem_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
     cuuint64_t strides[4] = {16, Wp * 8, 2 * Wp * 8, Hp * Wp * 8};
     cuuint32_t box[5] = {16, (cuuint32_t)(8 * S), 3, 16, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_32B;
+    if (raw) {
+      // dense view (pixel pair, image-row parity, image-row pair): element (k, p, q, y, n) =
+      //   base + n*Hp*Wp*8 + (2*y + q)*Wp*8 + p*16 + 2*k; the producer's coordinates (0, ow0, 0, oh0, n) address
+      //   pixel pair ow0 = pixel 2*ow0 and image row 2*oh0 of the padded tensor, i.e. the tile's top-left tap
+      dims[0] = 8, dims[1] = Wp / 2, dims[2] = 2, dims[3] = Hp / 2;
+      strides[0] = 16, strides[1] = Wp * 8, strides[2] = 2 * Wp * 8;
+      box[0] = 8, box[1] = pairs, box[2] = 2, box[3] = 17;
+      swz = CU_TENSOR_MAP_SWIZZLE_NONE;
+    }
     CUresult r = encode(&plan->tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d->in), dims, strides,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PB_CHECK(r == CUDA_SUCCESS, "conv(stem): cuTensorMapEncodeTiled(A, overlapping rows) failed with %d", (int)r);
   }
   {
