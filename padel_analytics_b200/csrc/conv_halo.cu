@@ -700,6 +700,107 @@ int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode)
   return 0;
 }
 
+// 1x1 / stride-1 layers through the same kernel (one tap, no halo): a CTA tile is 16 rows x 8S columns (up to 512
+// pixels, S accumulator sets) instead of the per-tap kernel's 128, and the whole filter bank (cin x cout, one box per
+// channel block) is fetched ONCE per CTA and stays in shared memory -- the per-tap kernel re-reads it from L2 for every
+// 128-pixel tile, as many bytes as the activations when cin ~ cout, and pays its fixed per-tile costs four times as
+// often.  Measured on the pose program (batch 32, profiles/r02_layers_final.txt): cin 32 -> 32 @320^2 152 -> 93 us; every
+// layer with cin >= 64 is 0-15 % SLOWER than on the per-tap kernel (whose flattened 128-pixel tiles waste nothing at the
+// image edges and whose K loop is deeper).  Default rule therefore: cin <= 32; PADEL_B200_CONV_HALO1=0 disables it, =2
+// takes every 1x1 layer whose bank fits next to two activation buffers.
+int conv_halo_1x1_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode) {
+  static const int enabled = [] {
+    const char* e = getenv("PADEL_B200_CONV_HALO1");
+    return e ? atoi(e) : 1;
+  }();
+  if (!enabled || d->ksize != 1 || d->stride != 1 || d->cout_pad > 256 || d->head_n != 0) return -1;
+  if (enabled == 1 && d->cin > 32) return -1;
+  // fp32 outputs (YOLO head maps, the TrackNet predictor) keep the per-tap kernel and its fp32 epilogue class
+  if (d->out_mode != PB_OUT_F16_NHWC && d->out_mode != PB_OUT_F16_NHWC_UP2) return -1;
+  ConvKParams& kp = plan->kp;  // common fields already filled by the caller
+  const int BN = d->cout_pad;
+  const uint32_t row_bytes = (uint32_t)kp.KB * 2u;
+  const int acc_cols = (BN + 31) / 32 * 32;
+  const size_t budget = 196 * 1024;
+  const uint32_t tap_bytes = (uint32_t)BN * row_bytes;
+  const uint32_t res_box = (tap_bytes + 1023u) & ~1023u;
+  const size_t res_total = (size_t)kp.kblocks * res_box;
+  if (kp.kblocks > kHaloMaxB || res_total > 120 * 1024) return -1;
+  int S = 0;
+  for (int s = 4; s >= 1; s >>= 1) {
+    if (s * acc_cols * 2 > 512) continue;  // keep >= 2 accumulator sets in TMEM
+    const uint32_t a_alloc = (16u * (uint32_t)(8 * s) * row_bytes + 1023u) & ~1023u;
+    if ((size_t)2 * a_alloc + res_total > budget) continue;
+    if (s > 1 && d->W <= 8 * (s / 2)) continue;  // a narrower tile already covers the row
+    S = s;
+    break;
+  }
+  if (S == 0) return -1;
+  const int P = 8 * S;
+  kp.pair = 0;
+  kp.b_resident = 1;
+  kp.hs_S = S;
+  kp.hs_P = P;
+  kp.hs_G = 1;
+  kp.hs_ntaps = 1;
+  kp.hs_sbo_rows = P;
+  kp.hs_x0 = 0;
+  kp.hs_y0 = 0;
+  kp.hs_tap_off[0] = 0;
+  kp.hs_tap_desc[0] = 0;
+  kp.BN = BN;
+  kp.n_ntiles = 1;
+  kp.halo_bytes = 16u * (uint32_t)P * row_bytes;
+  kp.hs_a_row_bytes = row_bytes;
+  kp.a_bytes = (kp.halo_bytes + 1023u) & ~1023u;
+  kp.b_tx_bytes = tap_bytes;
+  kp.b_bytes = res_box;
+  kp.b_stages = kp.kblocks;
+  {
+    const bool small = (size_t)2 * kp.a_bytes + res_total + sizeof(HaloSmemTail) + 1024 <= 108 * 1024 && S * acc_cols * 2 <= 256;
+    const size_t budget2 = small ? (size_t)108 * 1024 - sizeof(HaloSmemTail) - 1024 : budget;
+    int as = (int)((budget2 - res_total) / kp.a_bytes);
+    if (as > kHaloMaxA) as = kHaloMaxA;
+    if (as > 2 * kp.kblocks + 1) as = 2 * kp.kblocks + 1;
+    kp.a_stages = as < 2 ? 2 : as;
+  }
+  kp.acc_cols = acc_cols;
+  kp.acc_stages = 512 / (S * acc_cols);
+  if (kp.acc_stages > kConvMaxAcc) kp.acc_stages = kConvMaxAcc;
+  kp.idesc = umma_idesc_f16(BN, 0);
+  kp.tiles_w = (kp.Wo + 8 * S - 1) / (8 * S);
+  kp.tiles_h = (kp.Ho + 15) / 16;
+  kp.tiles_n = kp.N;
+  kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
+  halo_finish_config(plan);
+  plan->variant = 1;
+  const CUtensorMapSwizzle swz = kp.KB == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : kp.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                               : CU_TENSOR_MAP_SWIZZLE_32B;
+  {
+    const cuuint64_t C = (cuuint64_t)d->C, W = (cuuint64_t)d->W, H = (cuuint64_t)d->H;
+    cuuint64_t dims[5] = {C, W, 1, H, (cuuint64_t)d->N};
+    cuuint64_t strides[4] = {C * 2, W * C * 2, W * C * 2, H * W * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)kp.KB, (cuuint32_t)P, 1, 16, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&plan->tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d->in), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "conv(halo 1x1): cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)d->cout_pad, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * d->cout_pad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kp.KB, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&plan->tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d->weight), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "conv(halo 1x1): cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+  }
+  return 0;
+}
+
 // 3x3 / stride-2 conv over a whole C = 16 / 32 channel tensor.  The input is read through the pixel-pair view
 // (2C, W/2, 2, H/2, N) -- element (k, w2, ph, h2, n) = channel k % C of pixel (2*h2 + ph, 2*w2 + k / C) -- so one TMA
 // box (2C, 8S+1, 2, 17, 1) holds everything a 16 x 8S output tile needs, as rows of one PIXEL PAIR (4C bytes):

@@ -462,7 +462,9 @@ static int conv_plan_build_impl(const pb_conv_desc* d, ConvPlan* plan) {
     const char* e = getenv("PADEL_B200_CONV_HALO");
     const int mode = e ? atoi(e) : 2;
     if (mode == 1 || (mode == 2 && d->cout_pad <= 192)) {
-      const int rc = d->stride == 2 ? conv_halo_s2_setup(d, plan, encode) : conv_halo_setup(d, plan, encode);
+      const int rc = d->ksize == 1    ? conv_halo_1x1_setup(d, plan, encode)
+                     : d->stride == 2 ? conv_halo_s2_setup(d, plan, encode)
+                                      : conv_halo_setup(d, plan, encode);
       if (rc >= 0) return rc;
     }
   }

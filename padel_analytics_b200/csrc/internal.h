@@ -194,6 +194,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 int conv_halo_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);  // -1: not applicable
 int conv_stem_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);
 int conv_halo_s2_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);  // -1: not applicable
+int conv_halo_1x1_setup(const pb_conv_desc* d, ConvPlan* plan, EncodeTiledFn encode);  // -1: not applicable
 int conv_halo_launch(const ConvPlan* plan, cudaStream_t stream);
 int conv_plan_build(const pb_conv_desc* d, ConvPlan* plan);
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
