@@ -195,8 +195,11 @@ __device__ __forceinline__ void epi_add_res16(const uint4 (&rv)[2], float (&v)[1
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __half22float2(h2[j]);
-      v[8 * g + 2 * j] += f.x;
-      v[8 * g + 2 * j + 1] += f.y;
+      // __fadd_rn: never contracted with the activation's last multiply into an FMA -- the folded epilogue classes
+      // would otherwise round differently from the run-time epilogue (which the CTA-pair kernels use), and a frame's
+      // result must not depend on which of them its batch size selects (tests/test_full_size_gpu.py)
+      v[8 * g + 2 * j] = __fadd_rn(v[8 * g + 2 * j], f.x);
+      v[8 * g + 2 * j + 1] = __fadd_rn(v[8 * g + 2 * j + 1], f.y);
     }
   }
 }
