@@ -53,7 +53,8 @@ __device__ __forceinline__ HaloTile halo_decode(const ConvKParams& kp, int tile,
 
 // row_bytes 128 / 64 / 32: the swizzled K-major layouts.  row_bytes 16: the un-swizzled K-major layout -- 8-row core
 // matrices of 16-byte rows at a 16-byte pitch, 8-row groups `sbo_bytes` apart, the second 16-byte half of a K = 16 row
-// `lbo_bytes` further (16: the row that follows -- overlapping rows, used by the stem's raw-pixel operand).
+// `lbo_bytes` further (16: the row that follows -- overlapping rows, used by the stem's raw-pixel operand; the roles of
+// LBO and SBO in this layout were confirmed on hardware: swapping them fails tests/test_conv_gpu.py::test_stem_*).
 __device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes,
                                                   uint32_t lbo_bytes = 16) {
   const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : (row_bytes == 32 ? 6ull : 0ull));
@@ -223,9 +224,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (dbg) bwait += clock64() - ta;
           // Descriptor arithmetic is hoisted: per (channel block, weight stage) one base descriptor each; taps,
           // sub-tiles and k-steps only add precomputed 16-byte-unit offsets to the low word.
-          const uint64_t a_desc0 = (kp.dbg_flags & 8)  // bring-up: LBO / SBO roles swapped
-                                       ? umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), a_row_bytes, 16, sbo)
-                                       : umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), a_row_bytes, sbo);
+          const uint64_t a_desc0 = umma_desc_sbo(smem_u32(a_base + (size_t)ast * kp.a_bytes), a_row_bytes, sbo);
           for (int tg = 0; tg < tap_groups; ++tg) {
             const long long tb = dbg ? clock64() : 0;
             mbar_wait(&tail->b_full[bst], kp.b_resident ? 0u : bph);  // resident: filled once, phase 0 stays complete
