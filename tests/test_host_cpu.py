@@ -526,3 +526,35 @@ def test_block_postprocess_equals_per_result_postprocess():
     # concat pads to the largest count and keeps frame order
     c = ResultBlock.concat([blk[:10], blk[10:11], blk[11:]])
     assert np.array_equal(c.counts, blk.counts) and np.array_equal(c.rows, blk.rows[:, :c.rows.shape[1]])
+
+
+def test_block_postprocess_handles_empty_blocks_and_empty_shards():
+    """A rank may own no frames at all (more ranks than frames) and a batch may hold no detections."""
+    from types import SimpleNamespace
+
+    from padel_analytics_b200.engine.yolo_engine import ResultBlock
+    from padel_analytics_b200.trackers import runner as R
+    from padel_analytics_b200.trackers import sv_compat as sv
+    from padel_analytics_b200.trackers.keypoints_tracker import KeypointsTracker
+    from padel_analytics_b200.trackers.players_keypoints_tracker import PlayerKeypointsTracker
+    from padel_analytics_b200.trackers.players_tracker import PlayerTracker
+
+    def stub(cls, **attrs):
+        t = object.__new__(cls)
+        for k, v in attrs.items():
+            setattr(t, k, v)
+        return t
+
+    for ks, cls, extra in ((None, PlayerTracker, dict(polygon_zone=None, byte_track=sv.ByteTrack(frame_rate=30))),
+                           ((13, 3), PlayerKeypointsTracker, dict(train_image_size=1280)),
+                           ((12, 3), KeypointsTracker, {})):
+        trk = stub(cls, model=SimpleNamespace(kpt_shape=ks, names={0: "x"}), **extra)
+        rec = R._yolo_records([], trk)  # a shard without frames
+        blk = rec.to_results(trk)
+        assert len(blk) == 0 and list(blk) == []
+        args = () if cls is PlayerTracker else ((1080, 1920),)
+        assert trk.postprocess(blk, *args) == []
+        rowlen = rec.rows.shape[2]
+        none = ResultBlock(np.zeros((4, 1, rowlen), np.float32), np.zeros((4,), np.int32), ks, {0: "x"}, None)
+        out = trk.postprocess(ResultBlock.concat([blk, none, blk]), *args)  # frames without detections
+        assert len(out) == 4 and all(len(o.serialize()) == 0 for o in out)
