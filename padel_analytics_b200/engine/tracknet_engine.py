@@ -8,7 +8,6 @@ Network definition being replaced: /root/reference/trackers/ball_tracker/models.
 """
 from __future__ import annotations
 
-import ctypes as C
 import os
 
 import numpy as np
